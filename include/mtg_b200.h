@@ -1,0 +1,146 @@
+/*
+ * mtg_b200.h -- C-ABI of the B200-native batched linear min-derivative solver.
+ *
+ * Drop-in boundary for ONE path of ethz-asl/mav_trajectory_generation:
+ * PolynomialOptimization<N>::solveLinear() and the per-segment assembly feeding it.
+ * The reference has no FFI layer; what these entry points replace is the body of the
+ * following members (paths under mav_trajectory_generation/include/mav_trajectory_generation/):
+ *
+ *   mtg_solve_linear_batch_*      impl/polynomial_optimization_linear_impl.h:338-379 solveLinear()
+ *                                 + :285-305 updateSegmentTimes() (A^-1, Q per segment)
+ *                                 + :307-336 constructR()
+ *                                 + :262-283 updateSegmentsFromCompactConstraints()
+ *   mtg_coeffs_from_constraints_* impl/...linear_impl.h:499-508 setFreeConstraints()
+ *                                 -> :262-283 updateSegmentsFromCompactConstraints()
+ *   mtg_compute_cost_batch_*      impl/...linear_impl.h:123-140 computeCost()
+ *   mtg_problem_layout            impl/...linear_impl.h:181-260 setupConstraintReorderingMatrix()
+ *                                 (the 0/1 matrix C as one column index per row; host only)
+ *
+ * Conventions
+ *   - plain C, no torch / Eigen / STL types cross this boundary; every buffer is caller-owned.
+ *   - all arithmetic fp64; polynomial coefficients in INCREASING powers
+ *     (polynomial_optimization_linear.h:43-44).
+ *   - a "problem" is a constraint TOPOLOGY shared by the whole batch: N coefficients,
+ *     derivative_to_optimize r, K segments, D dimensions, and which derivatives each of the
+ *     K+1 vertices fixes.  Per trajectory only the segment times and the fixed constraint
+ *     VALUES differ (the reference re-uses one factorisation for all D for the same reason,
+ *     linear_impl.h:369-375).
+ *   - d_fixed / d_free use the reference's compact ordering: constraints sorted by
+ *     (vertex, derivative) (polynomial_optimization_linear.h:287-295), i.e. exactly
+ *     getFixedConstraints()/getFreeConstraints() (polynomial_optimization_linear.h:194-206).
+ *   - nothing here aborts or throws: argument errors return a negative code
+ *     (the reference CHECK-aborts, e.g. linear_impl.h:60,76,289,297); per-trajectory numeric
+ *     trouble is reported in status[] and never stops the batch.
+ *   - a handle is bound to one CUDA device and is single-caller (the reference object is not
+ *     thread-safe either); use one handle per host thread / per GPU.
+ *   - there is NO CPU fallback: every compute entry point launches sm_100a kernels or fails.
+ */
+#ifndef MTG_B200_H_
+#define MTG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTG_MAX_N 12 /* Polynomial::kMaxN, polynomial.h:44 */
+
+/* return codes */
+#define MTG_OK 0
+#define MTG_ERR_BAD_ARG (-1)      /* null pointer, odd N, r out of [0, N/2-1], K < 1, D < 1 ... */
+#define MTG_ERR_CUDA (-2)         /* CUDA runtime error; see mtg_last_error() */
+#define MTG_ERR_NO_DEVICE (-3)    /* no sm_100 device / extension cannot run */
+#define MTG_ERR_ALLOC (-4)
+
+/* per-trajectory status bits (status[b] == 0 means solved) */
+#define MTG_STATUS_BAD_TIME 1     /* some segment time <= 0 or NaN (reference: CHECK_GT, linear_impl.h:297) */
+#define MTG_STATUS_NOT_SPD 2      /* non-positive / NaN pivot in the R_pp factorisation */
+
+/* which kernel family a problem is routed to (introspection for tests / profiles) */
+#define MTG_KERNEL_WAYPOINT 1     /* thread-per-trajectory block-tridiagonal Cholesky, waypoint topology */
+#define MTG_KERNEL_GENERIC 2      /* arbitrary per-vertex masks, banded Cholesky in global scratch */
+#define MTG_KERNEL_NOFREE 3       /* n_free == 0: back-substitution only (linear_impl.h:343-349) */
+
+typedef struct mtg_handle mtg_handle;
+
+typedef struct mtg_problem {
+  int32_t N; /* coefficients per polynomial, even, 2..12   (template parameter _N, linear.h:45-51) */
+  int32_t r; /* derivative_to_optimize in [0, N/2-1]        (setupFromVertices arg, linear.h:67-69) */
+  int32_t K; /* number of segments (= vertices - 1) >= 1 */
+  int32_t D; /* dimensions >= 1 */
+  /* fixed_mask[(K+1)*(N/2)], row-major [vertex][derivative]: 1 = the vertex has a constraint on
+   * that derivative (Vertex::hasConstraint, vertex.h:84), 0 = free.  NULL selects the
+   * createRandomVertices / "waypoint" topology (vertex.cpp:27-82): first and last vertex fix
+   * derivatives 0..N/2-1, interior vertices fix position only. */
+  const uint8_t* fixed_mask;
+} mtg_problem;
+
+typedef struct mtg_layout {
+  int32_t n_all;    /* K*N          getNumberAllConstraints()   */
+  int32_t n_fixed;  /*              getNumberFixedConstraints() */
+  int32_t n_free;   /*              getNumberFreeConstraints()  */
+  int32_t kernel;   /* MTG_KERNEL_* this problem is routed to   */
+} mtg_layout;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int mtg_create(int device, mtg_handle** out);
+void mtg_destroy(mtg_handle* h);
+/* last error text of this handle (or of the last failed mtg_create when h == NULL) */
+const char* mtg_last_error(const mtg_handle* h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t mtg_launch_count(const mtg_handle* h);
+/* 1 when the visible device of the handle is compute capability 10.x */
+int mtg_device_is_sm100(const mtg_handle* h);
+
+/* ---- host-only layout: the constraint reordering (linear_impl.h:181-260) ---------------- */
+/* slot_col (nullable) receives K*N entries: row i*N+s of C (segment i, slot s; s < N/2 is
+ * derivative s at the segment start, s >= N/2 derivative s-N/2 at its end) has its single 1 in
+ * column slot_col[i*N+s]; columns [0,n_fixed) are d_fixed, [n_fixed, n_fixed+n_free) are d_free. */
+int mtg_problem_layout(const mtg_problem* p, mtg_layout* out, int32_t* slot_col);
+
+/* ---- the hot path, DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be 0) --- */
+/* seg_times [B][K], d_fixed [B][D][n_fixed]  ->  coeffs [B][K][D][N]
+ * optional: d_free [B][D][n_free], status [B] (int32). */
+int mtg_solve_linear_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                               const double* d_fixed, double* coeffs, double* d_free, int32_t* status,
+                               void* stream);
+
+/* updateSegmentsFromCompactConstraints for given d_free (setFreeConstraints path). */
+int mtg_coeffs_from_constraints_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B,
+                                          const double* seg_times, const double* d_fixed,
+                                          const double* d_free, double* coeffs, void* stream);
+
+/* computeCost(): cost[b] = 0.5 * sum_{segments, dims} c^T Q(T) c. */
+int mtg_compute_cost_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                               const double* coeffs, double* cost, void* stream);
+
+/* ---- the hot path, HOST pointers (what PolynomialOptimization<N>::solveLinear() calls) ---- */
+/* Same contract with host buffers; H2D, kernels and D2H are pipelined over internal streams and
+ * the call returns when the results are in the host buffers.  Pinned buffers (mtg_host_alloc)
+ * make the copies asynchronous; pageable buffers work but serialise. */
+int mtg_solve_linear_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                                    const double* d_fixed, double* coeffs, double* d_free,
+                                    int32_t* status);
+int mtg_coeffs_from_constraints_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B,
+                                               const double* seg_times, const double* d_fixed,
+                                               const double* d_free, double* coeffs);
+int mtg_compute_cost_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                                    const double* coeffs, double* cost);
+
+/* ---- memory helpers (so host code above the ABI needs no CUDA headers) -------------------- */
+void* mtg_host_alloc(mtg_handle* h, uint64_t bytes);   /* pinned */
+void mtg_host_free(mtg_handle* h, void* ptr);
+void* mtg_device_alloc(mtg_handle* h, uint64_t bytes);
+void mtg_device_free(mtg_handle* h, void* ptr);
+int mtg_memcpy_h2d(mtg_handle* h, void* dst, const void* src, uint64_t bytes, void* stream);
+int mtg_memcpy_d2h(mtg_handle* h, void* dst, const void* src, uint64_t bytes, void* stream);
+int mtg_stream_synchronize(mtg_handle* h, void* stream);
+
+/* library version (major*10000 + minor*100 + patch) */
+int mtg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTG_B200_H_ */

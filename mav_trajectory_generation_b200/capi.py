@@ -1,0 +1,212 @@
+"""ctypes binding of the C-ABI (include/mtg_b200.h) for tests, bench.py and smoke().
+
+This is plumbing only: device memory comes from torch tensors (data_ptr), streams from
+torch.cuda.  There is NO fallback: if libmtg_b200.so is missing or no sm_100 device is present
+every entry point raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+MTG_OK = 0
+KERNEL_WAYPOINT, KERNEL_GENERIC, KERNEL_NOFREE = 1, 2, 3
+STATUS_BAD_TIME, STATUS_NOT_SPD = 1, 2
+
+EXPORTED_SYMBOLS = [
+    "mtg_create", "mtg_destroy", "mtg_last_error", "mtg_launch_count", "mtg_device_is_sm100",
+    "mtg_problem_layout", "mtg_solve_linear_batch_f64", "mtg_coeffs_from_constraints_batch_f64",
+    "mtg_compute_cost_batch_f64", "mtg_solve_linear_batch_host_f64",
+    "mtg_coeffs_from_constraints_batch_host_f64", "mtg_compute_cost_batch_host_f64",
+    "mtg_host_alloc", "mtg_host_free", "mtg_device_alloc", "mtg_device_free", "mtg_memcpy_h2d",
+    "mtg_memcpy_d2h", "mtg_stream_synchronize", "mtg_version",
+]
+
+
+class MtgProblem(C.Structure):
+    _fields_ = [("N", C.c_int32), ("r", C.c_int32), ("K", C.c_int32), ("D", C.c_int32),
+                ("fixed_mask", C.POINTER(C.c_uint8))]
+
+
+class MtgLayout(C.Structure):
+    _fields_ = [("n_all", C.c_int32), ("n_fixed", C.c_int32), ("n_free", C.c_int32), ("kernel", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Load libmtg_b200.so (built in-tree by __graft_entry__.build()).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_CUDA
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA extension is the only compute path; there is no fallback)")
+    L = C.CDLL(path)
+    vp, i64, dp = C.c_void_p, C.c_int64, C.c_void_p
+    L.mtg_create.restype = C.c_int
+    L.mtg_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.mtg_destroy.argtypes = [vp]
+    L.mtg_destroy.restype = None
+    L.mtg_last_error.restype = C.c_char_p
+    L.mtg_last_error.argtypes = [vp]
+    L.mtg_launch_count.restype = i64
+    L.mtg_launch_count.argtypes = [vp]
+    L.mtg_device_is_sm100.argtypes = [vp]
+    L.mtg_problem_layout.argtypes = [C.POINTER(MtgProblem), C.POINTER(MtgLayout), vp]
+    L.mtg_solve_linear_batch_f64.argtypes = [vp, C.POINTER(MtgProblem), i64, dp, dp, dp, dp, dp, vp]
+    L.mtg_coeffs_from_constraints_batch_f64.argtypes = [vp, C.POINTER(MtgProblem), i64, dp, dp, dp, dp, vp]
+    L.mtg_compute_cost_batch_f64.argtypes = [vp, C.POINTER(MtgProblem), i64, dp, dp, dp, vp]
+    L.mtg_solve_linear_batch_host_f64.argtypes = [vp, C.POINTER(MtgProblem), i64, dp, dp, dp, dp, dp]
+    L.mtg_coeffs_from_constraints_batch_host_f64.argtypes = [vp, C.POINTER(MtgProblem), i64, dp, dp, dp, dp]
+    L.mtg_compute_cost_batch_host_f64.argtypes = [vp, C.POINTER(MtgProblem), i64, dp, dp, dp]
+    L.mtg_host_alloc.restype = vp
+    L.mtg_host_alloc.argtypes = [vp, C.c_uint64]
+    L.mtg_host_free.argtypes = [vp, vp]
+    L.mtg_device_alloc.restype = vp
+    L.mtg_device_alloc.argtypes = [vp, C.c_uint64]
+    L.mtg_device_free.argtypes = [vp, vp]
+    L.mtg_memcpy_h2d.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    L.mtg_memcpy_d2h.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    L.mtg_stream_synchronize.argtypes = [vp, vp]
+    L.mtg_version.restype = C.c_int
+    for name in EXPORTED_SYMBOLS:
+        getattr(L, name)  # AttributeError if the library does not export what the header declares
+    _lib = L
+    return L
+
+
+class Problem:
+    """A constraint topology: N, derivative_to_optimize r, K segments, D dimensions and the
+    per-vertex fixed mask ([K+1][N/2], None = createRandomVertices topology)."""
+
+    def __init__(self, N, r, K, D, fixed_mask=None):
+        self.N, self.r, self.K, self.D = int(N), int(r), int(K), int(D)
+        self._mask = None
+        self.c = MtgProblem(self.N, self.r, self.K, self.D, None)
+        if fixed_mask is not None:
+            self._mask = np.ascontiguousarray(fixed_mask, dtype=np.uint8).reshape(self.K + 1, self.N // 2)
+            self.c.fixed_mask = self._mask.ctypes.data_as(C.POINTER(C.c_uint8))
+        lay = MtgLayout()
+        slot = np.zeros(max(self.K * self.N, 1), dtype=np.int32)
+        rc = load().mtg_problem_layout(C.byref(self.c), C.byref(lay), slot.ctypes.data)
+        if rc != MTG_OK:
+            raise ValueError(f"invalid problem N={N} r={r} K={K} D={D} (rc={rc})")
+        self.n_all, self.n_fixed, self.n_free, self.kernel = lay.n_all, lay.n_fixed, lay.n_free, lay.kernel
+        self.slot_col = slot[: self.K * self.N]
+
+    @property
+    def bytes_per_trajectory(self):
+        """Algorithmic HBM bytes: seg_times + d_fixed in, coeffs out."""
+        return 8 * (self.K + self.D * self.n_fixed) + 8 * self.K * self.D * self.N
+
+
+class Solver:
+    """One handle on one CUDA device (single caller)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.mtg_create(int(device), C.byref(h))
+        if rc != MTG_OK:
+            raise RuntimeError(f"mtg_create failed (rc={rc}): {self.lib.mtg_last_error(None).decode()}")
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mtg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != MTG_OK:
+            raise RuntimeError(f"{what} failed (rc={rc}): {self.lib.mtg_last_error(self.h).decode()}")
+
+    @property
+    def launch_count(self):
+        return int(self.lib.mtg_launch_count(self.h))
+
+    # ---- device-pointer path (torch CUDA tensors, float64, contiguous) --------------------
+    def solve_linear(self, prob, seg_times, d_fixed, coeffs=None, d_free=None, status=None, stream=None):
+        import torch
+        B = seg_times.shape[0]
+        assert seg_times.is_cuda and seg_times.dtype == torch.float64 and seg_times.is_contiguous()
+        assert d_fixed.is_cuda and d_fixed.dtype == torch.float64 and d_fixed.is_contiguous()
+        assert tuple(seg_times.shape) == (B, prob.K) and tuple(d_fixed.shape) == (B, prob.D, prob.n_fixed)
+        if coeffs is None:
+            coeffs = torch.empty((B, prob.K, prob.D, prob.N), dtype=torch.float64, device=seg_times.device)
+        assert coeffs.is_contiguous() and tuple(coeffs.shape) == (B, prob.K, prob.D, prob.N)
+        s = stream if stream is not None else torch.cuda.current_stream(seg_times.device).cuda_stream
+        rc = self.lib.mtg_solve_linear_batch_f64(
+            self.h, C.byref(prob.c), B, seg_times.data_ptr(), d_fixed.data_ptr(), coeffs.data_ptr(),
+            d_free.data_ptr() if d_free is not None else None,
+            status.data_ptr() if status is not None else None, s)
+        self._check(rc, "mtg_solve_linear_batch_f64")
+        return coeffs
+
+    def coeffs_from_constraints(self, prob, seg_times, d_fixed, d_free, coeffs=None, stream=None):
+        import torch
+        B = seg_times.shape[0]
+        if coeffs is None:
+            coeffs = torch.empty((B, prob.K, prob.D, prob.N), dtype=torch.float64, device=seg_times.device)
+        s = stream if stream is not None else torch.cuda.current_stream(seg_times.device).cuda_stream
+        rc = self.lib.mtg_coeffs_from_constraints_batch_f64(
+            self.h, C.byref(prob.c), B, seg_times.data_ptr(), d_fixed.data_ptr(),
+            d_free.data_ptr() if d_free is not None else None, coeffs.data_ptr(), s)
+        self._check(rc, "mtg_coeffs_from_constraints_batch_f64")
+        return coeffs
+
+    def compute_cost(self, prob, seg_times, coeffs, cost=None, stream=None):
+        import torch
+        B = seg_times.shape[0]
+        if cost is None:
+            cost = torch.empty((B,), dtype=torch.float64, device=seg_times.device)
+        s = stream if stream is not None else torch.cuda.current_stream(seg_times.device).cuda_stream
+        rc = self.lib.mtg_compute_cost_batch_f64(self.h, C.byref(prob.c), B, seg_times.data_ptr(),
+                                                 coeffs.data_ptr(), cost.data_ptr(), s)
+        self._check(rc, "mtg_compute_cost_batch_f64")
+        return cost
+
+    # ---- host-pointer path (numpy arrays or pinned torch CPU tensors) ----------------------
+    @staticmethod
+    def _hptr(a):
+        if a is None:
+            return None
+        if isinstance(a, np.ndarray):
+            assert a.flags["C_CONTIGUOUS"]
+            return a.ctypes.data
+        assert a.is_contiguous() and not a.is_cuda
+        return a.data_ptr()
+
+    def solve_linear_host(self, prob, seg_times, d_fixed, coeffs, d_free=None, status=None):
+        B = seg_times.shape[0]
+        rc = self.lib.mtg_solve_linear_batch_host_f64(
+            self.h, C.byref(prob.c), B, self._hptr(seg_times), self._hptr(d_fixed), self._hptr(coeffs),
+            self._hptr(d_free), self._hptr(status))
+        self._check(rc, "mtg_solve_linear_batch_host_f64")
+        return coeffs
+
+    def coeffs_from_constraints_host(self, prob, seg_times, d_fixed, d_free, coeffs):
+        B = seg_times.shape[0]
+        rc = self.lib.mtg_coeffs_from_constraints_batch_host_f64(
+            self.h, C.byref(prob.c), B, self._hptr(seg_times), self._hptr(d_fixed), self._hptr(d_free),
+            self._hptr(coeffs))
+        self._check(rc, "mtg_coeffs_from_constraints_batch_host_f64")
+        return coeffs
+
+    def compute_cost_host(self, prob, seg_times, coeffs, cost):
+        B = seg_times.shape[0]
+        rc = self.lib.mtg_compute_cost_batch_host_f64(self.h, C.byref(prob.c), B, self._hptr(seg_times),
+                                                      self._hptr(coeffs), self._hptr(cost))
+        self._check(rc, "mtg_compute_cost_batch_host_f64")
+        return cost

@@ -1,0 +1,564 @@
+// mtg_capi.cu -- the C-ABI (include/mtg_b200.h): handle, host-side constraint layout,
+// kernel routing and the pipelined host-buffer entry points.  No CPU compute path exists
+// here: every mtg_*_batch_* call launches sm_100a kernels or returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mtg_b200.h"
+#include "mtg_generic_kernel.cuh"
+#include "mtg_waypoint_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Layout {
+  int n_all = 0, n_fixed = 0, n_free = 0, bw = 0;
+  bool waypoint = false;
+  std::vector<int32_t> slot_col;
+};
+
+struct CachedTopology {
+  std::vector<uint8_t> mask;  // canonical mask
+  int N = 0, K = 0;
+  Layout layout;
+  int32_t* d_slot_col = nullptr;
+};
+
+}  // namespace
+
+struct mtg_handle {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0;
+  size_t smem_optin = 0;
+  std::string error;
+  int64_t launches = 0;
+  std::vector<CachedTopology> topologies;
+  double* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // host-pointer pipeline
+  static constexpr int kPipe = 3;
+  cudaStream_t streams[kPipe] = {nullptr, nullptr, nullptr};
+  void* dev_buf[kPipe] = {nullptr, nullptr, nullptr};
+  size_t dev_buf_bytes[kPipe] = {0, 0, 0};
+};
+
+namespace {
+
+bool set_err(mtg_handle* h, const char* what, cudaError_t e) {
+  if (e == cudaSuccess) return false;
+  if (h) h->error = std::string(what) + ": " + cudaGetErrorString(e);
+  return true;
+}
+
+#define MTG_CUDA(h, call)                         \
+  do {                                            \
+    cudaError_t e__ = (call);                     \
+    if (set_err(h, #call, e__)) return MTG_ERR_CUDA; \
+  } while (0)
+
+bool valid_problem(const mtg_problem* p) {
+  if (!p) return false;
+  if (p->N < 2 || p->N > MTG_MAX_N || (p->N & 1)) return false;
+  if (p->r < 0 || p->r > p->N / 2 - 1) return false;  // CHECK at linear_impl.h:60
+  if (p->K < 1 || p->D < 1) return false;
+  return true;
+}
+
+std::vector<uint8_t> canonical_mask(const mtg_problem* p) {
+  const int h = p->N / 2;
+  std::vector<uint8_t> m(size_t(p->K + 1) * h, 0);
+  if (p->fixed_mask) {
+    for (size_t i = 0; i < m.size(); ++i) m[i] = p->fixed_mask[i] ? 1 : 0;
+  } else {
+    for (int v = 0; v <= p->K; ++v) {
+      m[size_t(v) * h] = 1;
+      if (v == 0 || v == p->K)
+        for (int k = 1; k < h; ++k) m[size_t(v) * h + k] = 1;
+    }
+  }
+  return m;
+}
+
+// The constraint reordering of linear_impl.h:181-260 in O(n): columns are the ranks of
+// (vertex, derivative) inside the sorted fixed / free sets (linear.h:287-295); row i*N+s is
+// slot s of segment i (s < h: vertex i, s >= h: vertex i+1; interior vertices appear twice,
+// :202-205).
+void compute_layout(int N, int K, const std::vector<uint8_t>& mask, Layout* L) {
+  const int h = N / 2;
+  std::vector<int32_t> col(size_t(K + 1) * h);
+  int nf = 0, np = 0;
+  for (size_t i = 0; i < mask.size(); ++i) (mask[i] ? nf : np)++;
+  int cf = 0, cp = 0;
+  for (size_t i = 0; i < mask.size(); ++i) col[i] = mask[i] ? cf++ : nf + cp++;
+  L->n_all = K * N;
+  L->n_fixed = nf;
+  L->n_free = np;
+  L->slot_col.resize(size_t(K) * N);
+  L->bw = 0;
+  for (int i = 0; i < K; ++i) {
+    int lo = 1 << 30, hi = -1;
+    for (int s = 0; s < N; ++s) {
+      const int v = s < h ? i : i + 1, k = s < h ? s : s - h;
+      const int c = col[size_t(v) * h + k];
+      L->slot_col[size_t(i) * N + s] = c;
+      if (c >= nf) { lo = std::min(lo, c); hi = std::max(hi, c); }
+    }
+    if (hi >= lo) L->bw = std::max(L->bw, hi - lo);
+  }
+  bool wp = K >= 2;
+  for (int v = 0; v <= K && wp; ++v)
+    for (int k = 0; k < h; ++k) {
+      const bool want = (k == 0) || v == 0 || v == K;
+      if ((mask[size_t(v) * h + k] != 0) != want) { wp = false; break; }
+    }
+  L->waypoint = wp && h >= 2;
+}
+
+// ---- waypoint kernel registry ---------------------------------------------------------
+typedef void (*WaypointKernel)(const mtg::WaypointParams);
+struct WaypointEntry {
+  int N, R, D, slots;
+  WaypointKernel fn;
+};
+#define MTG_WP(N_, R_, D_) \
+  { N_, R_, D_, mtg::waypoint_state_slots<N_, D_>(), mtg::waypoint_solve_kernel<N_, R_, D_> }
+const WaypointEntry kWaypointKernels[] = {
+    MTG_WP(10, 4, 3), MTG_WP(10, 4, 1), MTG_WP(10, 3, 3), MTG_WP(10, 2, 3),
+    MTG_WP(8, 3, 3),  MTG_WP(8, 3, 1),  MTG_WP(12, 5, 3),
+};
+
+const WaypointEntry* find_waypoint(const mtg_handle* h, const mtg_problem* p, const Layout& L) {
+  if (!L.waypoint) return nullptr;
+  for (const auto& e : kWaypointKernels)
+    if (e.N == p->N && e.R == p->r && e.D == p->D) {
+      const size_t smem = size_t(p->K - 1) * e.slots * 32 * sizeof(double);
+      if (smem <= h->smem_optin) return &e;
+    }
+  return nullptr;
+}
+
+int route(const mtg_handle* h, const mtg_problem* p, const Layout& L) {
+  if (L.n_free == 0) return MTG_KERNEL_NOFREE;
+  if (find_waypoint(h, p, L)) return MTG_KERNEL_WAYPOINT;
+  return MTG_KERNEL_GENERIC;
+}
+
+CachedTopology* get_topology(mtg_handle* h, const mtg_problem* p) {
+  std::vector<uint8_t> mask = canonical_mask(p);
+  for (auto& t : h->topologies)
+    if (t.N == p->N && t.K == p->K && t.mask == mask) return &t;
+  CachedTopology t;
+  t.N = p->N;
+  t.K = p->K;
+  t.mask = mask;
+  compute_layout(p->N, p->K, mask, &t.layout);
+  if (set_err(h, "cudaMalloc(slot_col)", cudaMalloc(&t.d_slot_col, sizeof(int32_t) * t.layout.slot_col.size())))
+    return nullptr;
+  if (set_err(h, "cudaMemcpy(slot_col)",
+              cudaMemcpy(t.d_slot_col, t.layout.slot_col.data(), sizeof(int32_t) * t.layout.slot_col.size(),
+                         cudaMemcpyHostToDevice)))
+    return nullptr;
+  if (h->topologies.size() >= 64) {  // bound the cache
+    cudaFree(h->topologies.front().d_slot_col);
+    h->topologies.erase(h->topologies.begin());
+  }
+  h->topologies.push_back(std::move(t));
+  return &h->topologies.back();
+}
+
+int ensure_scratch(mtg_handle* h, size_t bytes) {
+  if (bytes <= h->scratch_bytes) return MTG_OK;
+  // stream-ordered frees are not needed: scratch only grows and callers sync per handle
+  if (h->scratch) {
+    MTG_CUDA(h, cudaDeviceSynchronize());
+    cudaFree(h->scratch);
+    h->scratch = nullptr;
+    h->scratch_bytes = 0;
+  }
+  MTG_CUDA(h, cudaMalloc(&h->scratch, bytes));
+  h->scratch_bytes = bytes;
+  return MTG_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int64_t B, const double* times,
+                 const double* dfix, const double* dfree_in, double* coeffs, double* dfree, int32_t* status,
+                 cudaStream_t stream, bool backsub_only) {
+  const Layout& L = topo->layout;
+  if (B == 0) return MTG_OK;
+  const int kind = backsub_only ? MTG_KERNEL_NOFREE : route(h, p, L);
+  if (kind == MTG_KERNEL_WAYPOINT) {
+    const WaypointEntry* e = find_waypoint(h, p, L);
+    mtg::WaypointParams prm;
+    prm.K = p->K;
+    prm.n_fixed = L.n_fixed;
+    prm.B = B;
+    prm.times = times;
+    prm.dfix = dfix;
+    prm.coeffs = coeffs;
+    prm.dfree = dfree;
+    prm.status = status;
+    const size_t smem = size_t(p->K - 1) * e->slots * 32 * sizeof(double);
+    MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = (B + 31) / 32;
+    e->fn<<<(unsigned)blocks, 32, smem, stream>>>(prm);
+    MTG_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MTG_OK;
+  }
+  mtg::GenericParams prm;
+  prm.N = p->N;
+  prm.r = p->r;
+  prm.K = p->K;
+  prm.D = p->D;
+  prm.n_fixed = L.n_fixed;
+  prm.n_free = L.n_free;
+  prm.bw = L.bw;
+  prm.B = B;
+  prm.slot_col = topo->d_slot_col;
+  prm.times = times;
+  prm.dfix = dfix;
+  prm.dfree_in = dfree_in;
+  prm.coeffs = coeffs;
+  prm.dfree = dfree;
+  prm.status = status;
+  prm.scratch = nullptr;
+  prm.scratch_stride = 0;
+  const int threads = 128;
+  int64_t blocks = (B + threads - 1) / threads;
+  const int64_t max_blocks = int64_t(h->sm_count) * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (kind == MTG_KERNEL_NOFREE) {
+    if (L.n_free > 0 && dfree_in == nullptr) {
+      h->error = "d_free is required for back-substitution of a problem with free constraints";
+      return MTG_ERR_BAD_ARG;
+    }
+    mtg::backsub_kernel<<<(unsigned)blocks, threads, 0, stream>>>(prm);
+  } else {
+    const size_t per_thread = size_t(L.n_free) * (L.bw + 1 + p->D);
+    const size_t bytes = per_thread * size_t(blocks) * threads * sizeof(double);
+    const int rc = ensure_scratch(h, bytes);
+    if (rc != MTG_OK) return rc;
+    prm.scratch = h->scratch;
+    prm.scratch_stride = blocks * threads;
+    mtg::generic_solve_kernel<<<(unsigned)blocks, threads, 0, stream>>>(prm);
+  }
+  MTG_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return MTG_OK;
+}
+
+int ensure_pipe(mtg_handle* h, int i, size_t bytes) {
+  if (!h->streams[i]) MTG_CUDA(h, cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+  if (bytes > h->dev_buf_bytes[i]) {
+    if (h->dev_buf[i]) {
+      MTG_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+      cudaFree(h->dev_buf[i]);
+      h->dev_buf[i] = nullptr;
+      h->dev_buf_bytes[i] = 0;
+    }
+    MTG_CUDA(h, cudaMalloc(&h->dev_buf[i], bytes));
+    h->dev_buf_bytes[i] = bytes;
+  }
+  return MTG_OK;
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace
+
+extern "C" {
+
+int mtg_version(void) { return 100; }
+
+int mtg_create(int device, mtg_handle** out) {
+  if (!out) return MTG_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return MTG_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "device index out of range";
+    return MTG_ERR_BAD_ARG;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+    return MTG_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "this library contains sm_100a code only; device is sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor);
+    return MTG_ERR_NO_DEVICE;
+  }
+  mtg_handle* h = new (std::nothrow) mtg_handle();
+  if (!h) return MTG_ERR_ALLOC;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = h;
+  return MTG_OK;
+}
+
+void mtg_destroy(mtg_handle* h) {
+  if (!h) return;
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  for (auto& t : h->topologies) cudaFree(t.d_slot_col);
+  if (h->scratch) cudaFree(h->scratch);
+  for (int i = 0; i < mtg_handle::kPipe; ++i) {
+    if (h->dev_buf[i]) cudaFree(h->dev_buf[i]);
+    if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+  }
+  delete h;
+}
+
+const char* mtg_last_error(const mtg_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int64_t mtg_launch_count(const mtg_handle* h) { return h ? h->launches : 0; }
+
+int mtg_device_is_sm100(const mtg_handle* h) { return h && h->cc_major == 10; }
+
+int mtg_problem_layout(const mtg_problem* p, mtg_layout* out, int32_t* slot_col) {
+  if (!valid_problem(p) || !out) return MTG_ERR_BAD_ARG;
+  Layout L;
+  compute_layout(p->N, p->K, canonical_mask(p), &L);
+  out->n_all = L.n_all;
+  out->n_fixed = L.n_fixed;
+  out->n_free = L.n_free;
+  // routing without a device: assume the B200 opt-in shared memory limit (227 KB)
+  mtg_handle fake;
+  fake.smem_optin = 227 * 1024;
+  out->kernel = route(&fake, p, L);
+  if (slot_col) std::memcpy(slot_col, L.slot_col.data(), sizeof(int32_t) * L.slot_col.size());
+  return MTG_OK;
+}
+
+int mtg_solve_linear_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                               const double* d_fixed, double* coeffs, double* d_free, int32_t* status,
+                               void* stream) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  if (!valid_problem(p) || B < 0 || (B > 0 && (!seg_times || !d_fixed || !coeffs))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  DeviceGuard g(h->device);
+  CachedTopology* topo = get_topology(h, p);
+  if (!topo) return MTG_ERR_CUDA;
+  return launch_solve(h, p, topo, B, seg_times, d_fixed, nullptr, coeffs, d_free, status, (cudaStream_t)stream,
+                      false);
+}
+
+int mtg_coeffs_from_constraints_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B,
+                                          const double* seg_times, const double* d_fixed,
+                                          const double* d_free, double* coeffs, void* stream) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  if (!valid_problem(p) || B < 0 || (B > 0 && (!seg_times || !d_fixed || !coeffs))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  DeviceGuard g(h->device);
+  CachedTopology* topo = get_topology(h, p);
+  if (!topo) return MTG_ERR_CUDA;
+  return launch_solve(h, p, topo, B, seg_times, d_fixed, d_free, coeffs, nullptr, nullptr, (cudaStream_t)stream,
+                      true);
+}
+
+int mtg_compute_cost_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                               const double* coeffs, double* cost, void* stream) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  if (!valid_problem(p) || B < 0 || (B > 0 && (!seg_times || !coeffs || !cost))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  if (B == 0) return MTG_OK;
+  DeviceGuard g(h->device);
+  mtg::CostParams prm;
+  prm.N = p->N;
+  prm.r = p->r;
+  prm.K = p->K;
+  prm.D = p->D;
+  prm.B = B;
+  prm.times = seg_times;
+  prm.coeffs = coeffs;
+  prm.cost = cost;
+  const int threads = 128;
+  int64_t blocks = std::min<int64_t>((B + threads - 1) / threads, int64_t(h->sm_count) * 16);
+  mtg::cost_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(prm);
+  MTG_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return MTG_OK;
+}
+
+// ---- host-pointer variants: chunked H2D -> kernel -> D2H over kPipe streams ---------------
+static int host_pipeline(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                         const double* d_fixed, const double* d_free_in, double* coeffs, double* d_free_out,
+                         int32_t* status, bool backsub_only) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  if (!valid_problem(p) || B < 0 || (B > 0 && (!seg_times || !d_fixed || !coeffs))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  if (B == 0) return MTG_OK;
+  DeviceGuard g(h->device);
+  CachedTopology* topo = get_topology(h, p);
+  if (!topo) return MTG_ERR_CUDA;
+  const Layout& L = topo->layout;
+  const size_t K = p->K, D = p->D, N = p->N;
+  const size_t b_times = K * 8, b_fix = D * L.n_fixed * 8, b_free = D * size_t(L.n_free) * 8,
+               b_coef = K * D * N * 8;
+  const bool need_free_in = backsub_only && L.n_free > 0;
+  if (need_free_in && !d_free_in) {
+    h->error = "d_free is required";
+    return MTG_ERR_BAD_ARG;
+  }
+  // chunk so that the pipeline has work for every stream but stays in a few tens of MB
+  int64_t chunk = std::max<int64_t>(1, std::min<int64_t>((B + mtg_handle::kPipe - 1) / mtg_handle::kPipe, 32768));
+  if (B <= 4096) chunk = B;
+  int rc = MTG_OK;
+  int slot = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += chunk, slot = (slot + 1) % mtg_handle::kPipe) {
+    const int64_t nb = std::min<int64_t>(chunk, B - b0);
+    const size_t o_times = 0;
+    const size_t o_fix = align_up(o_times + b_times * nb);
+    const size_t o_freein = align_up(o_fix + b_fix * nb);
+    const size_t o_coef = align_up(o_freein + (need_free_in ? b_free * nb : 0));
+    const size_t o_free = align_up(o_coef + b_coef * nb);
+    const size_t o_stat = align_up(o_free + (d_free_out ? b_free * nb : 0));
+    const size_t total = align_up(o_stat + (status ? 4 * nb : 0));
+    rc = ensure_pipe(h, slot, total);
+    if (rc != MTG_OK) return rc;
+    cudaStream_t s = h->streams[slot];
+    char* base = static_cast<char*>(h->dev_buf[slot]);
+    MTG_CUDA(h, cudaMemcpyAsync(base + o_times, seg_times + b0 * K, b_times * nb, cudaMemcpyHostToDevice, s));
+    MTG_CUDA(h, cudaMemcpyAsync(base + o_fix, d_fixed + b0 * D * L.n_fixed, b_fix * nb, cudaMemcpyHostToDevice, s));
+    if (need_free_in)
+      MTG_CUDA(h, cudaMemcpyAsync(base + o_freein, d_free_in + b0 * D * L.n_free, b_free * nb,
+                                  cudaMemcpyHostToDevice, s));
+    rc = launch_solve(h, p, topo, nb, reinterpret_cast<double*>(base + o_times),
+                      reinterpret_cast<double*>(base + o_fix),
+                      need_free_in ? reinterpret_cast<double*>(base + o_freein) : nullptr,
+                      reinterpret_cast<double*>(base + o_coef),
+                      d_free_out ? reinterpret_cast<double*>(base + o_free) : nullptr,
+                      status ? reinterpret_cast<int32_t*>(base + o_stat) : nullptr, s, backsub_only);
+    if (rc != MTG_OK) return rc;
+    MTG_CUDA(h, cudaMemcpyAsync(coeffs + b0 * K * D * N, base + o_coef, b_coef * nb, cudaMemcpyDeviceToHost, s));
+    if (d_free_out && L.n_free > 0)
+      MTG_CUDA(h, cudaMemcpyAsync(d_free_out + b0 * D * L.n_free, base + o_free, b_free * nb,
+                                  cudaMemcpyDeviceToHost, s));
+    if (status) MTG_CUDA(h, cudaMemcpyAsync(status + b0, base + o_stat, 4 * nb, cudaMemcpyDeviceToHost, s));
+    // the buffer of this slot is reused kPipe chunks later: wait for it then
+    const int next = (slot + 1) % mtg_handle::kPipe;
+    if (b0 + chunk < B && h->streams[next]) MTG_CUDA(h, cudaStreamSynchronize(h->streams[next]));
+  }
+  for (int i = 0; i < mtg_handle::kPipe; ++i)
+    if (h->streams[i]) MTG_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  return MTG_OK;
+}
+
+int mtg_solve_linear_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                                    const double* d_fixed, double* coeffs, double* d_free, int32_t* status) {
+  return host_pipeline(h, p, B, seg_times, d_fixed, nullptr, coeffs, d_free, status, false);
+}
+
+int mtg_coeffs_from_constraints_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B,
+                                               const double* seg_times, const double* d_fixed,
+                                               const double* d_free, double* coeffs) {
+  return host_pipeline(h, p, B, seg_times, d_fixed, d_free, coeffs, nullptr, nullptr, true);
+}
+
+int mtg_compute_cost_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                                    const double* coeffs, double* cost) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  if (!valid_problem(p) || B < 0 || (B > 0 && (!seg_times || !coeffs || !cost))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  if (B == 0) return MTG_OK;
+  DeviceGuard g(h->device);
+  const size_t K = p->K, D = p->D, N = p->N;
+  const size_t o_coef = align_up(K * 8 * B), o_cost = align_up(o_coef + K * D * N * 8 * B);
+  int rc = ensure_pipe(h, 0, o_cost + 8 * B);
+  if (rc != MTG_OK) return rc;
+  cudaStream_t s = h->streams[0];
+  char* base = static_cast<char*>(h->dev_buf[0]);
+  MTG_CUDA(h, cudaMemcpyAsync(base, seg_times, K * 8 * B, cudaMemcpyHostToDevice, s));
+  MTG_CUDA(h, cudaMemcpyAsync(base + o_coef, coeffs, K * D * N * 8 * B, cudaMemcpyHostToDevice, s));
+  rc = mtg_compute_cost_batch_f64(h, p, B, reinterpret_cast<double*>(base), reinterpret_cast<double*>(base + o_coef),
+                                  reinterpret_cast<double*>(base + o_cost), s);
+  if (rc != MTG_OK) return rc;
+  MTG_CUDA(h, cudaMemcpyAsync(cost, base + o_cost, 8 * B, cudaMemcpyDeviceToHost, s));
+  MTG_CUDA(h, cudaStreamSynchronize(s));
+  return MTG_OK;
+}
+
+void* mtg_host_alloc(mtg_handle* h, uint64_t bytes) {
+  void* p = nullptr;
+  if (!h) return nullptr;
+  DeviceGuard g(h->device);
+  if (set_err(h, "cudaMallocHost", cudaMallocHost(&p, bytes ? bytes : 1))) return nullptr;
+  return p;
+}
+void mtg_host_free(mtg_handle* h, void* ptr) {
+  if (h && ptr) {
+    DeviceGuard g(h->device);
+    cudaFreeHost(ptr);
+  }
+}
+void* mtg_device_alloc(mtg_handle* h, uint64_t bytes) {
+  void* p = nullptr;
+  if (!h) return nullptr;
+  DeviceGuard g(h->device);
+  if (set_err(h, "cudaMalloc", cudaMalloc(&p, bytes ? bytes : 1))) return nullptr;
+  return p;
+}
+void mtg_device_free(mtg_handle* h, void* ptr) {
+  if (h && ptr) {
+    DeviceGuard g(h->device);
+    cudaFree(ptr);
+  }
+}
+int mtg_memcpy_h2d(mtg_handle* h, void* dst, const void* src, uint64_t bytes, void* stream) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  DeviceGuard g(h->device);
+  MTG_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return MTG_OK;
+}
+int mtg_memcpy_d2h(mtg_handle* h, void* dst, const void* src, uint64_t bytes, void* stream) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  DeviceGuard g(h->device);
+  MTG_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return MTG_OK;
+}
+int mtg_stream_synchronize(mtg_handle* h, void* stream) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  DeviceGuard g(h->device);
+  MTG_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return MTG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// mtg_device.cuh -- shared device helpers and the exact constant tables.
+//
+// Tables: H(1;r) = A(1)^-T Q(1;r) A(1)^-1 and A(1)^-1, exact rationals rounded once
+// (oracle/gen_tables.py).  The kernels never form A(T)^-1 or Q(T) numerically; they use
+//     A(T)^-1 = diag(T^-j) A(1)^-1 diag(T^(s mod h))
+//     H(T)    = T^(1-2r) diag(T^(s mod h)) H(1) diag(T^(s mod h))
+// which replace the reference's per-segment setupMappingMatrix / invertMappingMatrix /
+// computeQuadraticCostJacobian / Ai^T Q Ai (impl/polynomial_optimization_linear_impl.h
+// :111-121, :142-179, :567-583, :316-318) and avoid the cancellation of forming
+// A^-T Q A^-1 in floating point.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mtg_tables.h"
+
+#define MTG_MAX_N_HALF 6  // Polynomial::kMaxN / 2 (polynomial.h:44)
+
+namespace mtg {
+
+// Compile-time tables: element access with a compile-time index folds to an immediate /
+// constant-bank operand of the consuming DFMA (no load instruction).
+template <int N>
+struct A1Inv;
+template <int N, int R>
+struct H1;
+
+#define MTG_DEF_A1INV(N_)                                                              \
+  template <>                                                                          \
+  struct A1Inv<N_> {                                                                   \
+    static __host__ __device__ __forceinline__ constexpr double at(int r, int c) {     \
+      constexpr double t[] = MTG_A1INV_##N_;                                           \
+      return t[r * N_ + c];                                                            \
+    }                                                                                  \
+  };
+#define MTG_DEF_H1(N_, R_)                                                             \
+  template <>                                                                          \
+  struct H1<N_, R_> {                                                                  \
+    static __host__ __device__ __forceinline__ constexpr double at(int r, int c) {     \
+      constexpr double t[] = MTG_H1_##N_##_##R_;                                       \
+      return t[r * N_ + c];                                                            \
+    }                                                                                  \
+  };
+
+MTG_DEF_A1INV(2)
+MTG_DEF_A1INV(4)
+MTG_DEF_A1INV(6)
+MTG_DEF_A1INV(8)
+MTG_DEF_A1INV(10)
+MTG_DEF_A1INV(12)
+MTG_DEF_H1(2, 0)
+MTG_DEF_H1(4, 0)
+MTG_DEF_H1(4, 1)
+MTG_DEF_H1(6, 0)
+MTG_DEF_H1(6, 1)
+MTG_DEF_H1(6, 2)
+MTG_DEF_H1(8, 0)
+MTG_DEF_H1(8, 1)
+MTG_DEF_H1(8, 2)
+MTG_DEF_H1(8, 3)
+MTG_DEF_H1(10, 0)
+MTG_DEF_H1(10, 1)
+MTG_DEF_H1(10, 2)
+MTG_DEF_H1(10, 3)
+MTG_DEF_H1(10, 4)
+MTG_DEF_H1(12, 0)
+MTG_DEF_H1(12, 1)
+MTG_DEF_H1(12, 2)
+MTG_DEF_H1(12, 3)
+MTG_DEF_H1(12, 4)
+MTG_DEF_H1(12, 5)
+
+// Status bits (mirror include/mtg_b200.h).
+constexpr int kStatusBadTime = 1;
+constexpr int kStatusNotSpd = 2;
+
+// 1/sqrt(x) and 1/x on the fp64 pipe: MUFU seed + Newton steps (a few ulp; the block Cholesky
+// only needs the inverse pivots).
+__device__ __forceinline__ double fast_rsqrt(double x) { return rsqrt(x); }
+__device__ __forceinline__ double fast_rcp(double x) { return __drcp_rn(x); }
+
+}  // namespace mtg

@@ -1,0 +1,277 @@
+// mtg_generic_kernel.cuh -- K4: arbitrary per-vertex constraint masks (any Vertex::Vector the
+// reference accepts), runtime N / r / K / D; plus the back-substitution-only and cost kernels.
+//
+// One thread per trajectory, grid-stride.  The reduced system R_pp d_p = -R_pf d_f
+// (impl/polynomial_optimization_linear_impl.h:360-375) is assembled directly in banded
+// lower storage (free constraints sorted by (vertex, derivative) couple only inside one
+// segment, so the half bandwidth is <= 2h-1), factorised by a banded Cholesky and solved for
+// all D right-hand sides.  Scratch lives in global memory, interleaved by thread
+// (element e of thread t at scratch[e * stride + t]) so warp accesses coalesce.
+// The 0/1 reordering matrix C of the reference (linear_impl.h:181-260) is passed as one column
+// index per row (slot_col), built once per topology on the host.
+#pragma once
+
+#include "mtg_device.cuh"
+
+namespace mtg {
+
+// Runtime-indexed copies of the tables in constant memory (uniform index across a warp ->
+// broadcast).
+__constant__ double c_a1inv_2[] = MTG_A1INV_2;
+__constant__ double c_a1inv_4[] = MTG_A1INV_4;
+__constant__ double c_a1inv_6[] = MTG_A1INV_6;
+__constant__ double c_a1inv_8[] = MTG_A1INV_8;
+__constant__ double c_a1inv_10[] = MTG_A1INV_10;
+__constant__ double c_a1inv_12[] = MTG_A1INV_12;
+__constant__ double c_h1_2_0[] = MTG_H1_2_0;
+__constant__ double c_h1_4_0[] = MTG_H1_4_0;
+__constant__ double c_h1_4_1[] = MTG_H1_4_1;
+__constant__ double c_h1_6_0[] = MTG_H1_6_0;
+__constant__ double c_h1_6_1[] = MTG_H1_6_1;
+__constant__ double c_h1_6_2[] = MTG_H1_6_2;
+__constant__ double c_h1_8_0[] = MTG_H1_8_0;
+__constant__ double c_h1_8_1[] = MTG_H1_8_1;
+__constant__ double c_h1_8_2[] = MTG_H1_8_2;
+__constant__ double c_h1_8_3[] = MTG_H1_8_3;
+__constant__ double c_h1_10_0[] = MTG_H1_10_0;
+__constant__ double c_h1_10_1[] = MTG_H1_10_1;
+__constant__ double c_h1_10_2[] = MTG_H1_10_2;
+__constant__ double c_h1_10_3[] = MTG_H1_10_3;
+__constant__ double c_h1_10_4[] = MTG_H1_10_4;
+__constant__ double c_h1_12_0[] = MTG_H1_12_0;
+__constant__ double c_h1_12_1[] = MTG_H1_12_1;
+__constant__ double c_h1_12_2[] = MTG_H1_12_2;
+__constant__ double c_h1_12_3[] = MTG_H1_12_3;
+__constant__ double c_h1_12_4[] = MTG_H1_12_4;
+__constant__ double c_h1_12_5[] = MTG_H1_12_5;
+
+__device__ __forceinline__ const double* a1inv_table(int N) {
+  switch (N) {
+    case 2: return c_a1inv_2;
+    case 4: return c_a1inv_4;
+    case 6: return c_a1inv_6;
+    case 8: return c_a1inv_8;
+    case 10: return c_a1inv_10;
+    default: return c_a1inv_12;
+  }
+}
+
+__device__ __forceinline__ const double* h1_table(int N, int r) {
+  switch (N * 8 + r) {
+    case 2 * 8 + 0: return c_h1_2_0;
+    case 4 * 8 + 0: return c_h1_4_0;
+    case 4 * 8 + 1: return c_h1_4_1;
+    case 6 * 8 + 0: return c_h1_6_0;
+    case 6 * 8 + 1: return c_h1_6_1;
+    case 6 * 8 + 2: return c_h1_6_2;
+    case 8 * 8 + 0: return c_h1_8_0;
+    case 8 * 8 + 1: return c_h1_8_1;
+    case 8 * 8 + 2: return c_h1_8_2;
+    case 8 * 8 + 3: return c_h1_8_3;
+    case 10 * 8 + 0: return c_h1_10_0;
+    case 10 * 8 + 1: return c_h1_10_1;
+    case 10 * 8 + 2: return c_h1_10_2;
+    case 10 * 8 + 3: return c_h1_10_3;
+    case 10 * 8 + 4: return c_h1_10_4;
+    case 12 * 8 + 0: return c_h1_12_0;
+    case 12 * 8 + 1: return c_h1_12_1;
+    case 12 * 8 + 2: return c_h1_12_2;
+    case 12 * 8 + 3: return c_h1_12_3;
+    case 12 * 8 + 4: return c_h1_12_4;
+    default: return c_h1_12_5;
+  }
+}
+
+struct GenericParams {
+  int N, r, K, D;
+  int n_fixed, n_free, bw;
+  long long B;
+  const int* __restrict__ slot_col;   // [K*N]
+  const double* __restrict__ times;   // [B][K]
+  const double* __restrict__ dfix;    // [B][D][n_fixed]
+  const double* __restrict__ dfree_in;  // [B][D][n_free] (back-substitution-only kernel) or null
+  double* __restrict__ coeffs;        // [B][K][D][N]
+  double* __restrict__ dfree;         // [B][D][n_free] or null
+  int* __restrict__ status;           // [B] or null
+  double* __restrict__ scratch;       // per-thread interleaved scratch
+  long long scratch_stride;           // number of threads of the launch
+};
+
+// p = diag(T^-j) A(1)^-1 diag(T^(s mod h)) (C_i d)   (linear_impl.h:270-280), all segments.
+// value(col, d) supplies d_all[col].
+template <typename ValueFn>
+__device__ __forceinline__ void back_substitute(const GenericParams& prm, long long traj, ValueFn value) {
+  const int N = prm.N, h = N / 2, K = prm.K, D = prm.D;
+  const double* __restrict__ A1 = a1inv_table(N);
+  double* __restrict__ out = prm.coeffs + traj * (long long)K * D * N;
+  for (int i = 0; i < K; ++i) {
+    const double T = prm.times[traj * K + i];
+    const double iT = 1.0 / T;
+    double tp[MTG_MAX_N_HALF];
+    tp[0] = 1.0;
+    for (int k = 1; k < h; ++k) tp[k] = tp[k - 1] * T;
+    for (int d = 0; d < D; ++d) {
+      double sv[2 * MTG_MAX_N_HALF];
+      for (int s = 0; s < N; ++s) sv[s] = value(prm.slot_col[i * N + s], d);
+      double ip = 1.0;  // T^-j
+      for (int j = 0; j < N; ++j) {
+        double acc;
+        if (j < h) {
+          acc = sv[j] * A1[j * N + j];  // d_j / j!  (A^-1 is diagonal here)
+        } else {
+          acc = 0.0;
+          for (int s = 0; s < N; ++s) acc = fma(A1[j * N + s], tp[s < h ? s : s - h] * sv[s], acc);
+          acc *= ip;
+        }
+        out[((long long)i * D + d) * N + j] = acc;
+        ip *= iT;
+      }
+    }
+  }
+}
+
+// n_free == 0 shortcut (linear_impl.h:343-349) and setFreeConstraints (:499-508).
+__global__ void __launch_bounds__(128) backsub_kernel(const GenericParams prm) {
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x; traj < prm.B; traj += nthreads) {
+    const double* __restrict__ fx = prm.dfix + traj * (long long)prm.D * prm.n_fixed;
+    const double* __restrict__ fr =
+        prm.dfree_in ? prm.dfree_in + traj * (long long)prm.D * prm.n_free : nullptr;
+    const int nf = prm.n_fixed, np = prm.n_free;
+    int stat = 0;
+    for (int i = 0; i < prm.K; ++i)
+      if (!(prm.times[traj * prm.K + i] > 0.0)) stat |= kStatusBadTime;
+    back_substitute(prm, traj, [&](int col, int d) -> double {
+      return col < nf ? fx[d * nf + col] : fr[d * np + (col - nf)];
+    });
+    if (prm.status) prm.status[traj] = stat;
+  }
+}
+
+__global__ void __launch_bounds__(128) generic_solve_kernel(const GenericParams prm) {
+  const int N = prm.N, h = N / 2, K = prm.K, D = prm.D;
+  const int nf = prm.n_fixed, np = prm.n_free, bw = prm.bw, bw1 = prm.bw + 1;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const double* __restrict__ G = h1_table(N, prm.r);
+  double* __restrict__ scr = prm.scratch + tid;
+  const long long ss = prm.scratch_stride;
+  const long long rhs0 = (long long)np * bw1;
+#define BAND(i, k) scr[((long long)(i)*bw1 + (k)) * ss]
+#define RHS(i, d) scr[(rhs0 + (long long)(i)*D + (d)) * ss]
+
+  for (long long traj = tid; traj < prm.B; traj += nthreads) {
+    const double* __restrict__ fx = prm.dfix + traj * (long long)D * nf;
+    int stat = 0;
+    for (long long e = 0; e < rhs0 + (long long)np * D; ++e) scr[e * ss] = 0.0;
+
+    // ---- assemble R_pp (banded lower) and -R_pf d_f
+    for (int i = 0; i < K; ++i) {
+      const double T = prm.times[traj * K + i];
+      if (!(T > 0.0)) stat |= kStatusBadTime;
+      const double iT = 1.0 / T;
+      double sp[MTG_MAX_N_HALF];
+      sp[0] = 1.0;
+      for (int k = 1; k < h; ++k) sp[k] = sp[k - 1] * T;
+      double rho = T;  // T^(1-2r)
+      for (int k = 0; k < 2 * prm.r; ++k) rho *= iT;
+      for (int a = 0; a < N; ++a) {
+        const int ca = prm.slot_col[i * N + a] - nf;
+        if (ca < 0) continue;
+        const double fa = rho * sp[a < h ? a : a - h];
+        for (int b = 0; b < N; ++b) {
+          const int cb = prm.slot_col[i * N + b];
+          const double Hab = fa * sp[b < h ? b : b - h] * G[a * N + b];
+          if (cb >= nf) {
+            const int j = cb - nf;
+            if (j <= ca) BAND(ca, ca - j) += Hab;
+          } else {
+            for (int d = 0; d < D; ++d) RHS(ca, d) -= Hab * fx[d * nf + cb];
+          }
+        }
+      }
+    }
+
+    // ---- banded Cholesky, BAND(i,0) keeps the inverse pivot
+    for (int i = 0; i < np; ++i) {
+      const int j0 = i - bw > 0 ? i - bw : 0;
+      for (int j = j0; j <= i; ++j) {
+        double s = BAND(i, i - j);
+        for (int k = j0; k < j; ++k) {
+          if (j - k <= bw) s = fma(-BAND(i, i - k), BAND(j, j - k), s);
+        }
+        if (j < i) {
+          BAND(i, i - j) = s * BAND(j, 0);
+        } else {
+          if (!(s > 0.0)) stat |= kStatusNotSpd;
+          BAND(i, 0) = rsqrt(s);
+        }
+      }
+    }
+    // ---- forward / backward substitution for the D right-hand sides
+    for (int d = 0; d < D; ++d) {
+      for (int i = 0; i < np; ++i) {
+        const int j0 = i - bw > 0 ? i - bw : 0;
+        double s = RHS(i, d);
+        for (int k = j0; k < i; ++k) s = fma(-BAND(i, i - k), RHS(k, d), s);
+        RHS(i, d) = s * BAND(i, 0);
+      }
+      for (int i = np - 1; i >= 0; --i) {
+        const int k1 = i + bw < np - 1 ? i + bw : np - 1;
+        double s = RHS(i, d);
+        for (int k = i + 1; k <= k1; ++k) s = fma(-BAND(k, k - i), RHS(k, d), s);
+        RHS(i, d) = s * BAND(i, 0);
+      }
+    }
+    if (prm.dfree) {
+      double* __restrict__ df = prm.dfree + traj * (long long)D * np;
+      for (int d = 0; d < D; ++d)
+        for (int i = 0; i < np; ++i) df[d * np + i] = RHS(i, d);
+    }
+    back_substitute(prm, traj, [&](int col, int d) -> double {
+      return col < nf ? fx[d * nf + col] : RHS(col - nf, d);
+    });
+    if (prm.status) prm.status[traj] = stat;
+  }
+#undef BAND
+#undef RHS
+}
+
+// computeCost() (linear_impl.h:123-140): 0.5 * sum c^T Q(T) c with
+// Q[a][b] = 2 B(r,a) B(r,b) T^(a+b-2r+1) / (a+b-2r+1)   (:567-583).
+struct CostParams {
+  int N, r, K, D;
+  long long B;
+  const double* __restrict__ times;
+  const double* __restrict__ coeffs;
+  double* __restrict__ cost;
+};
+
+__global__ void __launch_bounds__(128) cost_kernel(const CostParams prm) {
+  const int N = prm.N, r = prm.r, K = prm.K, D = prm.D;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x; traj < prm.B; traj += nthreads) {
+    double total = 0.0;
+    for (int i = 0; i < K; ++i) {
+      const double T = prm.times[traj * K + i];
+      for (int d = 0; d < D; ++d) {
+        const double* __restrict__ c = prm.coeffs + ((traj * K + i) * D + d) * N;
+        double q[2 * MTG_MAX_N_HALF];
+        double tpow = 1.0;
+        for (int a = r; a < N; ++a) {
+          double bc = 1.0;  // B(r,a) = a!/(a-r)!
+          for (int k = 0; k < r; ++k) bc *= double(a - k);
+          q[a] = bc * c[a] * tpow;
+          tpow *= T;
+        }
+        double s = 0.0;
+        for (int a = r; a < N; ++a)
+          for (int b = r; b < N; ++b) s = fma(q[a] * q[b], 1.0 / double(a + b - 2 * r + 1), s);
+        total = fma(s, T, total);  // 0.5 * 2 * T^(1) * sum
+      }
+    }
+    prm.cost[traj] = total;
+  }
+}
+
+}  // namespace mtg
