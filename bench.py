@@ -1,0 +1,335 @@
+#!/usr/bin/env python3
+"""bench.py -- min-snap trajectories/sec of the batched solveLinear() hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" = one pass of the hot path over one batch of synthetic random-waypoint trajectories:
+BASELINE.json config C3 (262 144 trajectories, 16 segments, 3-D, N=10 min-snap, fp64) per GPU.
+Multi-GPU = independent shards, no data-path collective ("scaling": "weak"); time is the max
+over ranks.  Prints ONE JSON line (rank 0).
+
+  value      whole-job trajectories/s, inputs/outputs resident in HBM (CUDA events on the
+             launching stream, barrier + synchronize on both sides).
+  e2e        same metric through the host-pointer C-ABI call (what
+             PolynomialOptimization<N>::solveLinear() / BatchPolynomialOptimization calls):
+             pinned HOST buffers, H2D + kernels + D2H inside the timed region.
+  roofline   HBM: algorithmic bytes/launch (4568 B/trajectory) / kernel time,
+             against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the CPU oracle (restatement of the reference's Eigen path, oracle/oracle.cpp)
+             on all host cores, on a bounded sample of the same workload (rank 0, N=1 only).
+
+--impl reference times that CPU restatement itself (the reference needs Eigen/glog, absent
+from this image, so oracle/_ref cannot exist): kind "port".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONFIGS = {
+    # name: (N, r, K, D, batch per GPU)
+    "C3": (10, 4, 16, 3, 262144),
+    "C2": (10, 4, 8, 3, 65536),
+    "C4": (8, 3, 4, 3, 1048576),
+}
+METRIC = "min-snap trajectories/sec (N=10, 16-seg, 3D)"
+UNIT = "trajectories/s"
+
+
+def workload_name(cfg, B):
+    N, r, K, D, _ = CONFIGS[cfg]
+    return f"{cfg}: batch {B} random-waypoint {K}-segment {D}D N={N} derivative_to_optimize={r} fp64 per GPU"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(cfg):
+    """dram bytes per launch from the committed ncu --set full capture, or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(cfg)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_batch(torch, N, K, D, B, device, seed):
+    """Random-waypoint batch with the distribution of createRandomVertices(box +-10) +
+    estimateSegmentTimesNfabian(v=3, a=5) (reference vertex.cpp:27-82, :255-272), generated on the
+    device with a counter-based generator (the bit-exact mt19937 fixture is what tests/ use)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    pos = torch.rand((B, K + 1, D), generator=g, device=device, dtype=torch.float64) * 20.0 - 10.0
+    dist = (pos[:, 1:] - pos[:, :-1]).norm(dim=2).clamp_min(0.2)
+    v, a = 3.0, 5.0
+    times = dist / v * 2 * (1.0 + 6.5 * v / a * torch.exp(-dist / v * 2))
+    h = N // 2
+    nf = 2 * h + K - 1
+    dfix = torch.zeros((B, D, nf), device=device, dtype=torch.float64)
+    dfix[:, :, 0] = pos[:, 0]
+    dfix[:, :, h:h + K - 1] = pos[:, 1:K].transpose(1, 2)
+    dfix[:, :, h + K - 1] = pos[:, K]
+    return pos, times.contiguous(), dfix.contiguous()
+
+
+def cpu_baseline_sample(N, r, K, D, target_seconds=12.0, max_traj=400000):
+    """Times the CPU oracle (kind 'port') on a bounded sample, all host threads."""
+    import oracle_lib as O
+    O.build()
+    threads = O.hardware_threads() or os.cpu_count() or 1
+    probe = max(256, 64 * threads)
+    pos, times = O.make_waypoint_batch(K, D, probe, base_seed=1000)
+    _, s = O.solve_waypoint_batch(N, r, pos, times, n_threads=threads, mode=0, want_coeffs=False)
+    rate = probe / max(s, 1e-9)
+    n = int(min(max_traj, max(probe, rate * target_seconds)))
+    pos, times = O.make_waypoint_batch(K, D, n, base_seed=1000)
+    _, s = O.solve_waypoint_batch(N, r, pos, times, n_threads=threads, mode=0, want_coeffs=False)
+    return {"value": n / s, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} trajectories of the workload (mt19937 fixture seeds 1000+b), construct+setupFromVertices+"
+                      f"solveLinear per trajectory, {threads} host threads, {s:.2f} s wall"}, n, s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    N, r, K, D, B = CONFIGS[args.config]
+    if args.batch:
+        B = args.batch
+    import oracle_lib as O
+    O.build()
+    threads = O.hardware_threads() or os.cpu_count() or 1
+    # bounded sample per step: ~2 s of CPU work
+    probe = max(256, 64 * threads)
+    pos, times = O.make_waypoint_batch(K, D, probe, base_seed=1000)
+    _, s = O.solve_waypoint_batch(N, r, pos, times, n_threads=threads, mode=0, want_coeffs=False)
+    per_step = int(max(probe, min(200000, probe / max(s, 1e-9) * 2.0)))
+    pos, times = O.make_waypoint_batch(K, D, per_step, base_seed=1000)
+    for _ in range(args.warmup):
+        O.solve_waypoint_batch(N, r, pos, times, n_threads=threads, mode=0, want_coeffs=False)
+    t = 0.0
+    for _ in range(args.steps):
+        _, s = O.solve_waypoint_batch(N, r, pos, times, n_threads=threads, mode=0, want_coeffs=False)
+        t += s
+    value = per_step * args.steps / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, B), "sample_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{per_step} trajectories per step (bounded sample of the workload), CPU restatement "
+                                   f"of the reference Eigen path (Eigen/glog absent: reference itself unbuildable), "
+                                   f"{threads} host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import mav_trajectory_generation_b200 as m
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, r, K, D, B = CONFIGS[args.config]
+    if args.batch:
+        B = args.batch
+    prob = m.Problem(N, r, K, D)
+    solver = m.Solver(local)
+    _, times, dfix = synth_batch(torch, N, K, D, B, dev, seed=1234 + rank)
+    coeffs = torch.empty((B, K, D, N), dtype=torch.float64, device=dev)
+    status = torch.zeros((B,), dtype=torch.int32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ("value")
+    for _ in range(max(args.warmup, 3)):
+        solver.solve_linear(prob, times, dfix, coeffs=coeffs, status=status)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = solver.launch_count
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        starts[i].record()
+        solver.solve_linear(prob, times, dfix, coeffs=coeffs, status=status)
+        stops[i].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = solver.launch_count - launches0
+    total_ms = starts[0].elapsed_time(stops[-1])
+    kern_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops)) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    ok = bool((status == 0).all().item()) and bool(torch.isfinite(coeffs).all().item())
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---------------- end-to-end through the host-pointer C-ABI ("e2e")
+    h_times = torch.empty((B, K), dtype=torch.float64).pin_memory()
+    h_dfix = torch.empty((B, D, prob.n_fixed), dtype=torch.float64).pin_memory()
+    h_coeffs = torch.empty((B, K, D, N), dtype=torch.float64).pin_memory()
+    h_status = torch.empty((B,), dtype=torch.int32).pin_memory()
+    h_times.copy_(times)
+    h_dfix.copy_(dfix)
+    e2e_steps = max(1, min(args.steps, 5))
+    solver.solve_linear_host(prob, h_times, h_dfix, h_coeffs, status=h_status)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        solver.solve_linear_host(prob, h_times, h_dfix, h_coeffs, status=h_status)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te.item())
+    e2e_value = world * B * e2e_steps / t_e2e
+    e2e_ok = bool((h_status == 0).all().item()) and bool(torch.allclose(h_coeffs.to(dev), coeffs, rtol=0, atol=0))
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        bytes_per_launch = prob.bytes_per_trajectory * B
+        achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, B), "global_batch": world * B,
+                       "parallelism": f"shard{world}" if world > 1 else "single",
+                       "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2; no flush needed" %
+                             (bytes_per_launch / 1e6),
+                       "kernel": {1: "waypoint", 2: "generic", 3: "nofree"}[prob.kernel]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(args.config), "peak_source": peak_src,
+                         "bytes_per_trajectory": prob.bytes_per_trajectory, "kernel_ms": kern_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(8 * B * (K + D * prob.n_fixed)),
+                    "d2h_bytes_per_step": int(8 * B * K * D * N + 4 * B), "steps": e2e_steps,
+                    "bitwise_equal_to_device_path": e2e_ok},
+            "gpu_launches": int(launches), "clocks": clocks, "results_ok": ok,
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb, _, _ = cpu_baseline_sample(N, r, K, D)
+                line["cpu_baseline"] = cb
+            except Exception as e:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="override trajectories per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
