@@ -1,0 +1,63 @@
+// batch_polynomial_optimization.h -- B independent problems of ONE constraint topology solved in a
+// single pass of the B200 kernels.  This is the throughput entry point: the reference solves one
+// trajectory per PolynomialOptimization<N> object (its benchmark loops over objects,
+// src/polynomial_timing_evaluation.cpp:93-112); here the loop is the GPU grid.
+// Buffers are pinned host memory; solveLinear() pipelines H2D / kernels / D2H.
+#ifndef MAV_TRAJECTORY_GENERATION_BATCH_POLYNOMIAL_OPTIMIZATION_H_
+#define MAV_TRAJECTORY_GENERATION_BATCH_POLYNOMIAL_OPTIMIZATION_H_
+
+#include <vector>
+
+#include "mav_trajectory_generation/b200_core.h"
+
+namespace mav_trajectory_generation {
+
+template <int _N = 10>
+class BatchPolynomialOptimization {
+  static_assert(_N % 2 == 0, "The number of coefficients has to be even.");
+
+ public:
+  enum { N = _N };
+  static constexpr int kHighestDerivativeToOptimize = N / 2 - 1;
+
+  explicit BatchPolynomialOptimization(size_t dimension) : core_(N, dimension) {}
+
+  // Every problem must fix the same derivatives at the same vertices as vertices[0]; the
+  // constraint values and the segment times are per problem.
+  bool setupFromVertices(const std::vector<Vertex::Vector>& vertices,
+                         const std::vector<std::vector<double> >& segment_times,
+                         int derivative_to_optimize = kHighestDerivativeToOptimize) {
+    return core_.setupFromVertices(vertices, segment_times, derivative_to_optimize);
+  }
+  // createRandomVertices topology straight from flat arrays: positions[B][K+1][D], times[B][K];
+  // start/end derivatives 1..N/2-1 are zero (Vertex::makeStartOrEnd).
+  bool setupFromWaypoints(size_t batch, size_t n_segments, const double* positions, const double* segment_times,
+                          int derivative_to_optimize = kHighestDerivativeToOptimize) {
+    return core_.setupFromWaypoints(batch, n_segments, positions, segment_times, derivative_to_optimize);
+  }
+  bool solveLinear() { return core_.solveLinear(); }
+
+  size_t size() const { return core_.B_; }
+  size_t getDimension() const { return core_.dimension_; }
+  size_t getNumberSegments() const { return static_cast<size_t>(core_.topo_.K); }
+  size_t getNumberFixedConstraints() const { return static_cast<size_t>(core_.topo_.n_fixed); }
+  size_t getNumberFreeConstraints() const { return static_cast<size_t>(core_.topo_.n_free); }
+
+  void getSegments(size_t b, Segment::Vector* segments) const { core_.getSegments(b, CHECK_NOTNULL(segments)); }
+  void getTrajectory(size_t b, Trajectory* trajectory) const {
+    Segment::Vector s;
+    core_.getSegments(b, &s);
+    CHECK_NOTNULL(trajectory)->setSegments(s);
+  }
+  // Flat results: coefficients()[((b*K + segment)*D + dim)*N + power], status()[b].
+  const double* coefficients() const { return core_.coeffs_; }
+  const double* freeConstraints() const { return core_.d_free_; }  // [B][D][n_free]
+  const int32_t* status() const { return core_.status_; }
+  std::vector<double> computeCosts() const { return core_.computeCosts(); }
+
+ private:
+  b200::BatchCore core_;
+};
+
+}  // namespace mav_trajectory_generation
+#endif

@@ -1,0 +1,282 @@
+// test_host_api.cpp -- the reference's own gtest cases for the linear path
+// (mav_trajectory_generation/test/test_polynomial_optimization.cpp), re-stated against the
+// B200-backed PolynomialOptimization<N>.  `--cpu-only` runs the cases that need no device
+// (value types, fixtures, static helpers, layout); without it every solve goes through the GPU.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "mav_trajectory_generation/batch_polynomial_optimization.h"
+#include "mav_trajectory_generation/polynomial_optimization_linear.h"
+
+using namespace mav_trajectory_generation;
+
+static int g_failures = 0, g_checks = 0;
+#define EXPECT(cond)                                                        \
+  do {                                                                      \
+    ++g_checks;                                                             \
+    if (!(cond)) {                                                          \
+      ++g_failures;                                                         \
+      std::printf("EXPECT failed %s:%d: %s\n", __FILE__, __LINE__, #cond);  \
+    }                                                                       \
+  } while (0)
+#define EXPECT_NEAR(a, b, tol)                                                                     \
+  do {                                                                                             \
+    ++g_checks;                                                                                    \
+    if (!(std::abs((a) - (b)) <= (tol))) {                                                         \
+      ++g_failures;                                                                                \
+      std::printf("EXPECT_NEAR failed %s:%d: %.17g vs %.17g (tol %g)\n", __FILE__, __LINE__,       \
+                  double(a), double(b), double(tol));                                              \
+    }                                                                                              \
+  } while (0)
+
+constexpr int N = 10;
+
+struct Params {
+  int D, max_derivative, num_segments, seed;
+  double pos_bounds, v_max, a_max;
+};
+// test_polynomial_optimization.cpp:790-867
+static const Params kParams[] = {
+    {1, 4, 1, 100, 10.0, 3.0, 5.0},  {1, 4, 10, 102, 10.0, 3.0, 5.0}, {1, 4, 50, 103, 10.0, 3.0, 5.0},
+    {3, 4, 1, 104, 10.0, 3.0, 5.0},  {3, 4, 10, 105, 10.0, 3.0, 5.0}, {3, 4, 50, 106, 10.0, 3.0, 5.0},
+    {1, 2, 5, 107, 10.0, 1.0, 2.0},  {3, 2, 1, 108, 10.0, 1.0, 2.0},  {3, 2, 5, 109, 10.0, 1.0, 2.0},
+    {3, 3, 5, 110, 10.0, 1.0, 2.0},
+};
+
+static Vertex::Vector fixtureVertices(const Params& p) {
+  Eigen::VectorXd lo = Eigen::VectorXd::Constant(p.D, -p.pos_bounds), hi = Eigen::VectorXd::Constant(p.D, p.pos_bounds);
+  return createRandomVertices(getHighestDerivativeFromN(N), p.num_segments, lo, hi, p.seed);
+}
+
+// checkPath (test :113-174)
+static void checkPath(const Vertex::Vector& vertices, const std::vector<Segment>& segments) {
+  const double tol = 1e-6;
+  EXPECT(segments.size() == vertices.size() - 1);
+  for (size_t i = 0; i < segments.size(); ++i) {
+    const Segment& segment = segments[i];
+    for (int end = 0; end < 2; ++end) {
+      const Vertex& v = vertices[i + end];
+      const double t = end ? segment.getTime() : 0.0;
+      for (auto it = v.cBegin(); it != v.cEnd(); ++it) {
+        const Eigen::VectorXd actual = segment.evaluate(t, it->first);
+        for (int d = 0; d < segment.D(); ++d) EXPECT_NEAR(it->second[d], actual[d], tol);
+      }
+    }
+    if (i > 0)
+      for (int derivative = 0; derivative < N / 2; ++derivative) {
+        const Eigen::VectorXd a = segments[i - 1].evaluate(segments[i - 1].getTime(), derivative);
+        const Eigen::VectorXd b = segment.evaluate(0, derivative);
+        for (int d = 0; d < segment.D(); ++d) EXPECT_NEAR(a[d], b[d], tol);
+      }
+  }
+}
+
+static double costNumeric(const Trajectory& trajectory, int derivative, double dt) {
+  double cost = 0.0;
+  for (const Segment& s : trajectory.segments())
+    for (double t = 0.0; t < s.getTime(); t += dt) cost += s.evaluate(t, derivative).squaredNorm() * dt;
+  return cost;
+}
+
+static void testValueTypesAndFixtures() {
+  // createRandomVertices with std::mt19937(105): first vertex
+  Vertex::Vector v = fixtureVertices(kParams[4]);
+  Eigen::VectorXd p0;
+  EXPECT(v.size() == 11);
+  EXPECT(v[0].getConstraint(derivative_order::POSITION, &p0));
+  EXPECT(p0[0] == -3.4346932681103235 && p0[1] == 7.0047000485169981 && p0[2] == 2.9909075836621035);
+  EXPECT(v[0].getNumberOfConstraints() == 5 && v[5].getNumberOfConstraints() == 1 && v[10].hasConstraint(4));
+  // README example times (v = a = 2)
+  Vertex::Vector r;
+  Vertex s(3), m(3), e(3);
+  s.makeStartOrEnd(Eigen::Vector3d(0, 0, 1), derivative_order::SNAP);
+  m.addConstraint(derivative_order::POSITION, Eigen::Vector3d(1, 2, 3));
+  e.makeStartOrEnd(Eigen::Vector3d(2, 1, 5), derivative_order::SNAP);
+  r = {s, m, e};
+  const std::vector<double> t = estimateSegmentTimes(r, 2.0, 2.0);
+  EXPECT_NEAR(t[0], 3.97084783, 5e-9);
+  EXPECT_NEAR(t[1], 3.82413014, 5e-9);
+  // Polynomial: derivative coefficients and Horner evaluation
+  Eigen::VectorXd c(4);
+  c[0] = 1; c[1] = 2; c[2] = 3; c[3] = 4;
+  Polynomial poly(4, c);
+  EXPECT_NEAR(poly.evaluate(2.0, 0), 1 + 4 + 12 + 32, 1e-12);
+  EXPECT_NEAR(poly.evaluate(2.0, 1), 2 + 12 + 48, 1e-12);
+  EXPECT_NEAR(poly.getCoefficients(2)[1], 24.0, 0);
+  EXPECT(Polynomial::base_coefficients_(3, 5) == 60.0);
+  Eigen::VectorXd conv = Polynomial::convolve(c, c);
+  EXPECT(conv.size() == 7 && conv[6] == 16.0 && conv[0] == 1.0);
+}
+
+// AMatrixInversion (test :731-741) -- here A^-1 comes from the exact table scaling.
+static void testAMatrixInversion() {
+  for (double t = 1; t <= 60; t += 1) {
+    PolynomialOptimization<N>::SquareMatrix A, Ai;
+    PolynomialOptimization<N>::setupMappingMatrix(t, &A);
+    PolynomialOptimization<N>::invertMappingMatrix(A, &Ai);
+    // A * Ai == I, scaled per column of A (entries span 18 orders of magnitude at t = 60)
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0, mag = 0.0;
+        for (int k = 0; k < N; ++k) {
+          s += A(i, k) * Ai(k, j);
+          mag += std::abs(A(i, k) * Ai(k, j));
+        }
+        EXPECT_NEAR(s, i == j ? 1.0 : 0.0, 1e-12 * (1.0 + mag));
+      }
+  }
+  PolynomialOptimization<N>::SquareMatrix Q;
+  PolynomialOptimization<N>::computeQuadraticCostJacobian(4, 2.0, &Q);
+  EXPECT(Q(3, 3) == 0.0);
+  EXPECT_NEAR(Q(4, 4), 2.0 * 24 * 24 * 2.0, 1e-9);  // 2 * B(4,4)^2 * T^1 / 1
+}
+
+static void testLayoutOnly() {
+  const Params& p = kParams[4];
+  Vertex::Vector vertices = fixtureVertices(p);
+  b200::Topology topo;
+  b200::buildTopology(N, p.D, 4, &vertices, &topo);
+  EXPECT(topo.n_all == 100 && topo.n_fixed == 19 && topo.n_free == 36);
+  EXPECT(topo.kernel == 1);
+}
+
+// TwoVerticesSetup (test :743-787): Matlab golden coefficients.
+static void testTwoVerticesSetup() {
+  Vertex start(1), goal(1);
+  for (int d = 0; d <= 4; ++d) start.addConstraint(d, 0.0);
+  goal = start;
+  goal.addConstraint(derivative_order::POSITION, 5.0);
+  PolynomialOptimization<10> opt(1);
+  Vertex::Vector vertices{start, goal};
+  opt.setupFromVertices(vertices, {5.0 * 2.0 / 2.0}, derivative_order::SNAP);
+  EXPECT(opt.solveLinear());
+  Segment::Vector segments;
+  opt.getSegments(&segments);
+  checkPath(vertices, segments);
+  const double matlab[10] = {-0.000000000000004, 0.000000000000004, -0.000000000000006, 0.000000000000003,
+                             -0.000000000000001, 0.201600000000015, -0.134400000000012, 0.034560000000004,
+                             -0.004032000000000, 0.000179200000000};
+  const Eigen::VectorXd coeffs = segments[0].getPolynomialsRef()[0].getCoefficients();
+  for (int i = 0; i < 10; ++i) EXPECT_NEAR(coeffs[i], matlab[i], 2e-14);
+  EXPECT(opt.getNumberFreeConstraints() == 0 && opt.getNumberFixedConstraints() == 10);
+}
+
+// UnconstrainedLinearEstimateSegmentTimes (test :271-306)
+static void testUnconstrainedLinear(const Params& p) {
+  Vertex::Vector vertices = fixtureVertices(p);
+  std::vector<double> times = estimateSegmentTimes(vertices, p.v_max, p.a_max);
+  PolynomialOptimization<N> opt(p.D);
+  EXPECT(opt.setupFromVertices(vertices, times, p.max_derivative));
+  EXPECT(opt.solveLinear());
+  EXPECT(opt.getLastStatus() == 0);
+  Segment::Vector segments;
+  opt.getSegments(&segments);
+  Trajectory trajectory;
+  opt.getTrajectory(&trajectory);
+  EXPECT(trajectory.K() == p.num_segments && trajectory.D() == p.D && trajectory.N() == N);
+  checkPath(vertices, segments);
+  const double cost = opt.computeCost();
+  const double numeric = costNumeric(trajectory, p.max_derivative, 0.001);
+  EXPECT(std::abs(numeric - cost) <= numeric * 0.1);  // checkCost (:176-197)
+  // updateSegmentTimes + solveLinear (the nonlinear optimiser's inner step): stretching time lowers cost
+  std::vector<double> slower = times;
+  for (double& t : slower) t *= 1.5;
+  opt.updateSegmentTimes(slower);
+  EXPECT(opt.solveLinear());
+  EXPECT(opt.computeCost() < cost);
+}
+
+// ConstraintPacking (test :505-564)
+static void testConstraintPacking(const Params& p) {
+  Eigen::VectorXd lo = Eigen::VectorXd::Constant(p.D, -50.0), hi = Eigen::VectorXd::Constant(p.D, 50.0);
+  for (size_t rep = 0; rep < 5; ++rep) {
+    Vertex::Vector vertices = createRandomVertices(p.max_derivative, p.num_segments, lo, hi, 12345 + rep);
+    std::vector<double> times = estimateSegmentTimes(vertices, 3.0, 5.0);
+    PolynomialOptimization<N> opt(p.D);
+    opt.setupFromVertices(vertices, times);
+    opt.solveLinear();
+    Segment::Vector segments;
+    opt.getSegments(&segments);
+    std::vector<Eigen::VectorXd> fixed, free_c;
+    opt.getFixedConstraints(&fixed);
+    opt.getFreeConstraints(&free_c);
+    Eigen::MatrixXd M, A_inv, A, M_pinv;
+    opt.getM(&M);
+    opt.getAInverse(&A_inv);
+    opt.getA(&A);
+    opt.getMpinv(&M_pinv);
+    EXPECT(int(fixed.size()) == p.D && int(free_c.size()) == p.D);
+    for (int d = 0; d < p.D; ++d) {
+      Eigen::VectorXd d_all(fixed[d].size() + free_c[d].size());
+      for (int i = 0; i < fixed[d].size(); ++i) d_all[i] = fixed[d][i];
+      for (int i = 0; i < free_c[d].size(); ++i) d_all[fixed[d].size() + i] = free_c[d][i];
+      Eigen::VectorXd Md = M * d_all;
+      Eigen::VectorXd pp = A_inv * Md;
+      Eigen::VectorXd d_un = A * pp;
+      Eigen::VectorXd d_re = M_pinv * d_un;
+      for (int i = 0; i < d_all.size(); ++i) EXPECT_NEAR(d_all[i], d_re[i], 1e-6);
+      for (size_t j = 0; j < segments.size(); ++j) {
+        const Eigen::VectorXd p_seg = segments[j][d].getCoefficients(0);
+        for (int k = 0; k < N; ++k) EXPECT_NEAR(p_seg[k], pp[j * N + k], 1e-6);
+      }
+    }
+    // setFreeConstraints with the optimum reproduces the solution
+    Segment::Vector again;
+    opt.setFreeConstraints(free_c);
+    opt.getSegments(&again);
+    for (size_t j = 0; j < segments.size(); ++j)
+      for (int d = 0; d < p.D; ++d) {
+        const Eigen::VectorXd a = segments[j][d].getCoefficients(0), b = again[j][d].getCoefficients(0);
+        for (int k = 0; k < N; ++k) EXPECT_NEAR(a[k], b[k], 1e-9 * (1.0 + std::abs(a[k])));
+      }
+  }
+}
+
+// The batch entry point returns, per problem, exactly what the single-problem object returns.
+static void testBatchMatchesSingle() {
+  const int D = 3, K = 8, B = 37;
+  Eigen::VectorXd lo = Eigen::VectorXd::Constant(D, -10.0), hi = Eigen::VectorXd::Constant(D, 10.0);
+  std::vector<Vertex::Vector> all_vertices;
+  std::vector<std::vector<double> > all_times;
+  for (int b = 0; b < B; ++b) {
+    all_vertices.push_back(createRandomVertices(4, K, lo, hi, 1000 + b));
+    all_times.push_back(estimateSegmentTimes(all_vertices.back(), 3.0, 5.0));
+  }
+  BatchPolynomialOptimization<N> batch(D);
+  EXPECT(batch.setupFromVertices(all_vertices, all_times, derivative_order::SNAP));
+  EXPECT(batch.solveLinear());
+  EXPECT(batch.size() == size_t(B));
+  std::vector<double> costs = batch.computeCosts();
+  for (int b = 0; b < B; ++b) {
+    EXPECT(batch.status()[b] == 0);
+    PolynomialOptimization<N> opt(D);
+    opt.setupFromVertices(all_vertices[b], all_times[b], derivative_order::SNAP);
+    opt.solveLinear();
+    Segment::Vector single, from_batch;
+    opt.getSegments(&single);
+    batch.getSegments(b, &from_batch);
+    EXPECT(single.size() == from_batch.size());
+    for (size_t j = 0; j < single.size(); ++j) EXPECT(single[j] == from_batch[j]);  // bitwise
+    EXPECT_NEAR(costs[b], opt.computeCost(), 1e-12 * std::abs(costs[b]));
+    if (b == 0) checkPath(all_vertices[b], from_batch);
+  }
+}
+
+int main(int argc, char** argv) {
+  const bool cpu_only = argc > 1 && std::strcmp(argv[1], "--cpu-only") == 0;
+  testValueTypesAndFixtures();
+  testAMatrixInversion();
+  testLayoutOnly();
+  if (!cpu_only) {
+    testTwoVerticesSetup();
+    for (const Params& p : kParams) testUnconstrainedLinear(p);
+    for (const Params& p : kParams) testConstraintPacking(p);
+    testBatchMatchesSingle();
+  }
+  std::printf("%s: %d checks, %d failures\n", cpu_only ? "cpu-only" : "full", g_checks, g_failures);
+  return g_failures == 0 ? 0 : 1;
+}
