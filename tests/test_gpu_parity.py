@@ -50,7 +50,11 @@ def test_waypoint_kernel_matches_oracle(solver, oracle, N, r, K, D, B):
     assert prob.kernel == m.KERNEL_WAYPOINT
     assert (status == 0).all()
     err = global_rel_err(out, ref)
-    tol = TOL if (N, r) in ((10, 4), (8, 3)) else 5e-9  # other (N,r): the reference's own rounding dominates
+    # The 1e-10 bar is for the BASELINE fixtures (3-D, box +-10, v 3, a 5 => T >~ 3 s).  Elsewhere the
+    # reference-order arithmetic itself is further than 1e-10 from the exact answer (1-D fixtures have
+    # short segments, T ~ 1 s; r < N/2-1 cancels harder): there the oracle comparison is loose and
+    # test_gpu_vs_truth pins the kernel to the exact answer instead.
+    tol = TOL if ((N, r) in ((10, 4), (8, 3)) and D == 3) else 5e-9
     assert err.max() <= tol, f"max global-relative error {err.max():.3e}"
 
 
@@ -71,3 +75,223 @@ def test_generic_kernel_matches_oracle_on_waypoint_mask(solver, oracle):
     assert (status.cpu().numpy() == 0).all()
     err = global_rel_err(out.cpu().numpy(), ref)
     assert err.max() <= TOL, f"{err.max():.3e}"
+
+
+@pytest.mark.parametrize("N,r,K,D,seed", [(10, 4, 16, 3, 1000), (10, 4, 16, 1, 1003), (10, 3, 5, 3, 110), (10, 2, 5, 3, 109),
+                                          (12, 5, 6, 3, 3), (8, 3, 4, 3, 1002)])
+def test_gpu_vs_truth(solver, oracle, N, r, K, D, seed):
+    """Against the 60-digit solve of the same equations (oracle/truth.py): the kernels' exact-table
+    formulation is ~1e-13 from the exact answer, i.e. closer than the reference's own arithmetic."""
+    import os
+    import sys
+    import torch
+    import mav_trajectory_generation_b200 as m
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import truth
+    B = 3
+    pos, times = oracle.make_waypoint_batch(K, D, B, base_seed=seed)
+    prob = m.Problem(N, r, K, D)
+    out = solver.solve_linear(prob, torch.from_numpy(times).cuda(),
+                              torch.from_numpy(oracle.waypoint_d_fixed(N, pos)).cuda()).cpu().numpy()
+    for b in range(B):
+        mask, values = oracle.waypoint_problem(N, pos[b])
+        tru, _ = truth.solve(N, r, mask, values, times[b])
+        err = np.abs(out[b] - tru).max() / np.abs(tru).max()
+        assert err <= 2e-12, (b, err)
+
+
+def test_generic_kernel_arbitrary_masks(solver, oracle):
+    """Arbitrary Vertex constraint sets (interior velocity fixed, free end derivatives, non-zero end
+    derivatives), several N: the generic kernel against the oracle and the d_free output against the
+    oracle's getFreeConstraints."""
+    import torch
+    import mav_trajectory_generation_b200 as m
+    rng = np.random.RandomState(11)
+    for trial in range(12):
+        N = int(rng.choice([6, 8, 10, 12]))
+        h = N // 2
+        K = int(rng.randint(2, 9))
+        D = int(rng.randint(1, 4))
+        B = 33
+        mask = (rng.rand(K + 1, h) < 0.35).astype(np.uint8)
+        mask[:, 0] = 1
+        mask[0, :] = 1
+        prob = m.Problem(N, h - 1, K, D, fixed_mask=mask)
+        if prob.n_free == 0:
+            continue
+        assert prob.kernel in (m.KERNEL_GENERIC, m.KERNEL_WAYPOINT)
+        times = rng.uniform(2.0, 6.0, size=(B, K))
+        values = rng.uniform(-2, 2, size=(B, K + 1, h, D)) * mask[None, :, :, None]
+        values[:, :, 0, :] = rng.uniform(-10, 10, size=(B, K + 1, D))
+        ref = np.zeros((B, K, D, N))
+        dfix = np.zeros((B, D, prob.n_fixed))
+        dfree_ref = np.zeros((B, D, prob.n_free))
+        for b in range(B):
+            res = oracle.solve(N, h - 1, mask, values[b], times[b])
+            ref[b], dfix[b], dfree_ref[b] = res["coeffs"], res["d_fixed"], res["d_free"]
+        status = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+        dfree = torch.zeros((B, D, prob.n_free), dtype=torch.float64, device="cuda")
+        out = solver.solve_linear(prob, torch.from_numpy(times).cuda(), torch.from_numpy(dfix).cuda(), d_free=dfree,
+                                  status=status)
+        torch.cuda.synchronize()
+        assert (status.cpu().numpy() == 0).all()
+        err = global_rel_err(out.cpu().numpy(), ref)
+        assert err.max() <= 5e-9, (trial, N, K, D, err.max())
+        scale = np.abs(dfree_ref).max()
+        assert np.abs(dfree.cpu().numpy() - dfree_ref).max() <= 5e-9 * scale
+
+
+def test_waypoint_nonzero_end_derivatives_and_dfree(solver, oracle):
+    """Start/end vertices with NON-zero velocity..snap (the general makeStartOrEnd-free case) through
+    the waypoint kernel; also checks the optional d_free output."""
+    import torch
+    import mav_trajectory_generation_b200 as m
+    rng = np.random.RandomState(5)
+    N, r, K, D, B = 10, 4, 6, 3, 65
+    h = N // 2
+    pos, times = oracle.make_waypoint_batch(K, D, B, base_seed=2000)
+    sd = rng.uniform(-1, 1, size=(B, h - 1, D))
+    ed = rng.uniform(-1, 1, size=(B, h - 1, D))
+    dfix = oracle.waypoint_d_fixed(N, pos, sd, ed)
+    prob = m.Problem(N, r, K, D)
+    assert prob.kernel == m.KERNEL_WAYPOINT
+    ref = np.zeros((B, K, D, N))
+    dfree_ref = np.zeros((B, D, prob.n_free))
+    for b in range(B):
+        mask, values = oracle.waypoint_problem(N, pos[b])
+        values[0, 1:, :] = sd[b]
+        values[-1, 1:, :] = ed[b]
+        res = oracle.solve(N, r, mask, values, times[b])
+        ref[b], dfree_ref[b] = res["coeffs"], res["d_free"]
+        np.testing.assert_array_equal(res["d_fixed"], dfix[b])
+    dfree = torch.zeros((B, D, prob.n_free), dtype=torch.float64, device="cuda")
+    out = solver.solve_linear(prob, torch.from_numpy(times).cuda(), torch.from_numpy(dfix).cuda(), d_free=dfree)
+    torch.cuda.synchronize()
+    assert global_rel_err(out.cpu().numpy(), ref).max() <= TOL
+    assert np.abs(dfree.cpu().numpy() - dfree_ref).max() <= 1e-9 * np.abs(dfree_ref).max()
+
+
+def test_status_flags_and_edge_cases(solver, oracle):
+    import torch
+    import mav_trajectory_generation_b200 as m
+    N, r, K, D, B = 10, 4, 4, 3, 40
+    pos, times = oracle.make_waypoint_batch(K, D, B)
+    times[3, 1] = 0.0       # reference: CHECK_GT(segment_time, 0) aborts (linear_impl.h:297)
+    times[7, 2] = -1.0
+    times[9, 0] = float("nan")
+    prob = m.Problem(N, r, K, D)
+    status = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+    out = solver.solve_linear(prob, torch.from_numpy(times).cuda(), torch.from_numpy(oracle.waypoint_d_fixed(N, pos)).cuda(),
+                              status=status)
+    st = status.cpu().numpy()
+    bad = [3, 7, 9]
+    assert all(st[b] & m.STATUS_BAD_TIME for b in bad)
+    good = [b for b in range(B) if b not in bad]
+    assert (st[good] == 0).all()
+    ref, _ = oracle.solve_waypoint_batch(N, r, pos[good], times[good])
+    assert global_rel_err(out.cpu().numpy()[good], ref).max() <= TOL
+    # empty batch is a no-op
+    empty = solver.solve_linear(prob, torch.zeros((0, K), dtype=torch.float64, device="cuda"),
+                                torch.zeros((0, D, prob.n_fixed), dtype=torch.float64, device="cuda"))
+    assert empty.shape[0] == 0
+
+
+def test_nofree_backsub_and_cost(solver, oracle):
+    """n_free == 0 shortcut (linear_impl.h:343-349), setFreeConstraints path and computeCost()."""
+    import torch
+    import mav_trajectory_generation_b200 as m
+    # fully constrained single segment, N = 12, 4-D (the reference's feasibility-test usage)
+    rng = np.random.RandomState(2)
+    N, r, K, D, B = 12, 5, 1, 4, 50
+    h = N // 2
+    mask = np.ones((2, h), dtype=np.uint8)
+    prob = m.Problem(N, r, K, D, fixed_mask=mask)
+    assert prob.kernel == m.KERNEL_NOFREE
+    values = rng.uniform(-1, 1, size=(B, 2, h, D))
+    times = rng.uniform(1.0, 5.0, size=(B, 1))
+    ref = np.zeros((B, K, D, N))
+    dfix = np.zeros((B, D, prob.n_fixed))
+    cost_ref = np.zeros(B)
+    for b in range(B):
+        res = oracle.solve(N, r, mask, values[b], times[b])
+        ref[b], dfix[b], cost_ref[b] = res["coeffs"], res["d_fixed"], res["cost"]
+    t_d = torch.from_numpy(times).cuda()
+    out = solver.solve_linear(prob, t_d, torch.from_numpy(dfix).cuda())
+    assert global_rel_err(out.cpu().numpy(), ref).max() <= TOL
+    cost = solver.compute_cost(prob, t_d, out).cpu().numpy()
+    np.testing.assert_allclose(cost, cost_ref, rtol=1e-9)
+    # setFreeConstraints path on a problem with free constraints: feed the oracle's optimum back
+    N, r, K, D, B = 10, 4, 5, 3, 20
+    pos, times = oracle.make_waypoint_batch(K, D, B)
+    prob = m.Problem(N, r, K, D)
+    ref = np.zeros((B, K, D, N))
+    dfree = np.zeros((B, D, prob.n_free))
+    cost_ref = np.zeros(B)
+    for b in range(B):
+        mask, values = oracle.waypoint_problem(N, pos[b])
+        res = oracle.solve(N, r, mask, values, times[b])
+        ref[b], dfree[b], cost_ref[b] = res["coeffs"], res["d_free"], res["cost"]
+    t_d = torch.from_numpy(times).cuda()
+    out = solver.coeffs_from_constraints(prob, t_d, torch.from_numpy(oracle.waypoint_d_fixed(N, pos)).cuda(),
+                                         torch.from_numpy(dfree).cuda())
+    assert global_rel_err(out.cpu().numpy(), ref).max() <= TOL
+    np.testing.assert_allclose(solver.compute_cost(prob, t_d, out).cpu().numpy(), cost_ref, rtol=1e-8)
+
+
+def test_host_pointer_path_bitwise_equals_device_path(solver, oracle):
+    """mtg_solve_linear_batch_host_f64 (what the C++ solveLinear() calls): chunked H2D/solve/D2H gives
+    bit-identical results to the device-pointer call (each trajectory is solved independently)."""
+    import torch
+    import mav_trajectory_generation_b200 as m
+    N, r, K, D, B = 10, 4, 8, 3, 100003  # > one pipeline chunk, ragged
+    rng = np.random.RandomState(0)
+    pos = rng.uniform(-10, 10, size=(B, K + 1, D))
+    dist = np.maximum(np.linalg.norm(np.diff(pos, axis=1), axis=2), 0.2)
+    times = dist / 3.0 * 2 * (1.0 + 6.5 * 3.0 / 5.0 * np.exp(-dist / 3.0 * 2))
+    dfix = oracle.waypoint_d_fixed(N, pos)
+    prob = m.Problem(N, r, K, D)
+    dev = solver.solve_linear(prob, torch.from_numpy(times).cuda(), torch.from_numpy(dfix).cuda()).cpu().numpy()
+    host = np.zeros((B, K, D, N))
+    status = np.full(B, -1, dtype=np.int32)
+    solver.solve_linear_host(prob, np.ascontiguousarray(times), dfix, host, status=status)
+    assert (status == 0).all()
+    assert np.array_equal(host, dev)
+    ref, _ = oracle.solve_waypoint_batch(N, r, pos[:512], times[:512], n_threads=oracle.hardware_threads())
+    assert global_rel_err(host[:512], ref).max() <= TOL
+
+
+def test_full_size_properties_c3(solver):
+    """BASELINE C3 at full size (262 144 x 16 segments): size-independent properties instead of an
+    oracle pass -- position constraints met, derivatives 0..4 continuous at every interior vertex,
+    zero end derivatives, shard-concatenation == whole-batch (bitwise), computeCost linear in D."""
+    import torch
+    import mav_trajectory_generation_b200 as m
+    import bench
+    N, r, K, D, B = 10, 4, 16, 3, 262144
+    dev = torch.device("cuda:0")
+    pos, times, dfix = bench.synth_batch(torch, N, K, D, B, dev, seed=7)
+    prob = m.Problem(N, r, K, D)
+    status = torch.full((B,), -1, dtype=torch.int32, device=dev)
+    out = solver.solve_linear(prob, times, dfix, status=status)
+    assert bool((status == 0).all())
+    # evaluate derivatives at t = 0 and t = T with torch (independent of the kernels)
+    T = times[:, :, None, None]                                   # [B][K][1][1]
+    powers = torch.arange(N, device=dev, dtype=torch.float64)
+    scale = pos.abs().max()
+    for k in range(5):
+        fall = torch.ones(N, device=dev, dtype=torch.float64)
+        for q in range(k):
+            fall = fall * (powers - q).clamp_min(0)
+        at0 = out[..., k] * fall[k]
+        atT = (out * fall * T ** (powers - k).clamp_min(0)).sum(dim=-1)   # [B][K][D]
+        tol = 1e-7 * float(scale)
+        if k == 0:
+            assert (at0 - pos[:, :-1]).abs().max() <= tol and (atT - pos[:, 1:]).abs().max() <= tol
+        else:
+            assert at0[:, 0].abs().max() <= tol and atT[:, -1].abs().max() <= tol
+        assert (atT[:, :-1] - at0[:, 1:]).abs().max() <= tol   # continuity at interior vertices
+    # sharding: solving two halves separately gives the same bits
+    half = B // 2
+    a = solver.solve_linear(prob, times[:half].contiguous(), dfix[:half].contiguous())
+    b = solver.solve_linear(prob, times[half:].contiguous(), dfix[half:].contiguous())
+    assert torch.equal(torch.cat([a, b]), out)
