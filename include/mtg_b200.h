@@ -93,6 +93,12 @@ int64_t mtg_launch_count(const mtg_handle* h);
 /* 1 when the visible device of the handle is compute capability 10.x */
 int mtg_device_is_sm100(const mtg_handle* h);
 
+/* tuning knobs (results are identical to rounding; used by tests and profiles)
+ *   MTG_OPT_WAYPOINT_VARIANT: 0 = default (two lanes per trajectory, twisted factorisation),
+ *                             1 = one thread per trajectory, 2 = twisted. */
+#define MTG_OPT_WAYPOINT_VARIANT 1
+int mtg_set_option(mtg_handle* h, int key, int value);
+
 /* ---- host-only layout: the constraint reordering (linear_impl.h:181-260) ---------------- */
 /* slot_col (nullable) receives K*N entries: row i*N+s of C (segment i, slot s; s < N/2 is
  * derivative s at the segment start, s >= N/2 derivative s-N/2 at its end) has its single 1 in

@@ -14,6 +14,7 @@ from . import _build
 MTG_OK = 0
 KERNEL_WAYPOINT, KERNEL_GENERIC, KERNEL_NOFREE = 1, 2, 3
 STATUS_BAD_TIME, STATUS_NOT_SPD = 1, 2
+OPT_WAYPOINT_VARIANT = 1
 
 EXPORTED_SYMBOLS = [
     "mtg_create", "mtg_destroy", "mtg_last_error", "mtg_launch_count", "mtg_device_is_sm100",
@@ -21,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "mtg_compute_cost_batch_f64", "mtg_solve_linear_batch_host_f64",
     "mtg_coeffs_from_constraints_batch_host_f64", "mtg_compute_cost_batch_host_f64",
     "mtg_host_alloc", "mtg_host_free", "mtg_device_alloc", "mtg_device_free", "mtg_memcpy_h2d",
-    "mtg_memcpy_d2h", "mtg_stream_synchronize", "mtg_version",
+    "mtg_memcpy_d2h", "mtg_stream_synchronize", "mtg_version", "mtg_set_option",
 ]
 
 
@@ -74,6 +75,7 @@ def load():
     L.mtg_memcpy_d2h.argtypes = [vp, vp, vp, C.c_uint64, vp]
     L.mtg_stream_synchronize.argtypes = [vp, vp]
     L.mtg_version.restype = C.c_int
+    L.mtg_set_option.argtypes = [vp, C.c_int, C.c_int]
     for name in EXPORTED_SYMBOLS:
         getattr(L, name)  # AttributeError if the library does not export what the header declares
     _lib = L
@@ -131,6 +133,9 @@ class Solver:
     def _check(self, rc, what):
         if rc != MTG_OK:
             raise RuntimeError(f"{what} failed (rc={rc}): {self.lib.mtg_last_error(self.h).decode()}")
+
+    def set_option(self, key, value):
+        self._check(self.lib.mtg_set_option(self.h, int(key), int(value)), "mtg_set_option")
 
     @property
     def launch_count(self):

@@ -12,6 +12,7 @@
 
 #include "../../include/mtg_b200.h"
 #include "mtg_generic_kernel.cuh"
+#include "mtg_twisted_kernel.cuh"
 #include "mtg_waypoint_kernel.cuh"
 
 namespace {
@@ -40,6 +41,7 @@ struct mtg_handle {
   size_t smem_optin = 0;
   std::string error;
   int64_t launches = 0;
+  int waypoint_variant = 0;  // MTG_OPT_WAYPOINT_VARIANT
   std::vector<CachedTopology> topologies;
   double* scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -126,10 +128,14 @@ void compute_layout(int N, int K, const std::vector<uint8_t>& mask, Layout* L) {
 typedef void (*WaypointKernel)(const mtg::WaypointParams);
 struct WaypointEntry {
   int N, R, D, slots;
-  WaypointKernel fn;
+  WaypointKernel fn;          // one thread per trajectory
+  WaypointKernel fn_twisted;  // two lanes per trajectory (twisted factorisation)
 };
-#define MTG_WP(N_, R_, D_) \
-  { N_, R_, D_, mtg::waypoint_state_slots<N_, D_>(), mtg::waypoint_solve_kernel<N_, R_, D_> }
+#define MTG_WP(N_, R_, D_)                                                                   \
+  {                                                                                          \
+    N_, R_, D_, mtg::waypoint_state_slots<N_, D_>(), mtg::waypoint_solve_kernel<N_, R_, D_>, \
+        mtg::twisted_solve_kernel<N_, R_, D_>                                                \
+  }
 const WaypointEntry kWaypointKernels[] = {
     MTG_WP(10, 4, 3), MTG_WP(10, 4, 1), MTG_WP(10, 3, 3), MTG_WP(10, 2, 3),
     MTG_WP(8, 3, 3),  MTG_WP(8, 3, 1),  MTG_WP(12, 5, 3),
@@ -139,7 +145,7 @@ const WaypointEntry* find_waypoint(const mtg_handle* h, const mtg_problem* p, co
   if (!L.waypoint) return nullptr;
   for (const auto& e : kWaypointKernels)
     if (e.N == p->N && e.R == p->r && e.D == p->D) {
-      const size_t smem = size_t(p->K - 1) * e.slots * 32 * sizeof(double);
+      const size_t smem = size_t((p->K + 1) / 2 - 1) * e.slots * 32 * sizeof(double);  // twisted variant
       if (smem <= h->smem_optin) return &e;
     }
   return nullptr;
@@ -217,10 +223,19 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
     prm.coeffs = coeffs;
     prm.dfree = dfree;
     prm.status = status;
-    const size_t smem = size_t(p->K - 1) * e->slots * 32 * sizeof(double);
-    MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t blocks = (B + 31) / 32;
-    e->fn<<<(unsigned)blocks, 32, smem, stream>>>(prm);
+    const size_t smem_v1 = size_t(p->K - 1) * e->slots * 32 * sizeof(double);
+    const bool use_v1 = h->waypoint_variant == 1 && smem_v1 <= h->smem_optin;
+    if (use_v1) {
+      MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v1));
+      const int64_t blocks = (B + 31) / 32;
+      e->fn<<<(unsigned)blocks, 32, smem_v1, stream>>>(prm);
+    } else {
+      const size_t smem = size_t((p->K + 1) / 2 - 1) * e->slots * 32 * sizeof(double);
+      MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn_twisted, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+      const int64_t blocks = (B + 15) / 16;
+      e->fn_twisted<<<(unsigned)blocks, 32, smem, stream>>>(prm);
+    }
     MTG_CUDA(h, cudaGetLastError());
     h->launches++;
     return MTG_OK;
@@ -342,6 +357,16 @@ const char* mtg_last_error(const mtg_handle* h) { return h ? h->error.c_str() : 
 int64_t mtg_launch_count(const mtg_handle* h) { return h ? h->launches : 0; }
 
 int mtg_device_is_sm100(const mtg_handle* h) { return h && h->cc_major == 10; }
+
+int mtg_set_option(mtg_handle* h, int key, int value) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  if (key == MTG_OPT_WAYPOINT_VARIANT && value >= 0 && value <= 2) {
+    h->waypoint_variant = value;
+    return MTG_OK;
+  }
+  h->error = "unknown option";
+  return MTG_ERR_BAD_ARG;
+}
 
 int mtg_problem_layout(const mtg_problem* p, mtg_layout* out, int32_t* slot_col) {
   if (!valid_problem(p) || !out) return MTG_ERR_BAD_ARG;

@@ -19,9 +19,10 @@ def global_rel_err(a, b):
     return num / den
 
 
-def run_waypoint(solver, oracle, N, r, K, D, B, base_seed=1000, want_free=True):
+def run_waypoint(solver, oracle, N, r, K, D, B, base_seed=1000, want_free=True, variant=0):
     import torch
     import mav_trajectory_generation_b200 as m
+    solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, variant)
     pos, times = oracle.make_waypoint_batch(K, D, B, base_seed=base_seed)
     ref, _ = oracle.solve_waypoint_batch(N, r, pos, times, n_threads=oracle.hardware_threads())
     prob = m.Problem(N, r, K, D)
@@ -32,21 +33,35 @@ def run_waypoint(solver, oracle, N, r, K, D, B, base_seed=1000, want_free=True):
     dfree = torch.zeros((B, D, max(prob.n_free, 1)), dtype=torch.float64, device="cuda") if want_free else None
     out = solver.solve_linear(prob, t_d, f_d, d_free=dfree, status=status)
     torch.cuda.synchronize()
+    solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, 0)
     return prob, pos, times, ref, out.cpu().numpy(), status.cpu().numpy(), (dfree.cpu().numpy() if want_free else None)
 
 
+@pytest.mark.parametrize("variant", [1, 2])  # 1: thread per trajectory, 2: twisted (two lanes per trajectory)
 @pytest.mark.parametrize("N,r,K,D,B", [
     (10, 4, 16, 3, 2048),   # C3 headline shape
     (10, 4, 8, 3, 2048),    # C2
     (8, 3, 4, 3, 4096),     # C4
-    (10, 4, 2, 3, 257),     # C1 shape, ragged batch
+    (10, 4, 2, 3, 257),     # C1 shape, ragged batch: only the middle vertex
+    (10, 4, 3, 3, 129),     # unbalanced halves (1 + 0 vertices)
+    (10, 4, 5, 3, 131),     # unbalanced halves (2 + 1)
+    (10, 4, 50, 3, 48),     # the reference's largest test case (twisted only: v1 state does not fit)
     (10, 4, 16, 1, 300),
     (10, 3, 5, 3, 300),
     (12, 5, 6, 3, 300),
 ])
-def test_waypoint_kernel_matches_oracle(solver, oracle, N, r, K, D, B):
+def test_waypoint_kernel_matches_oracle(solver, oracle, N, r, K, D, B, variant):
     import mav_trajectory_generation_b200 as m
-    prob, pos, times, ref, out, status, dfree = run_waypoint(solver, oracle, N, r, K, D, B)
+    prob, pos, times, ref, out, status, dfree = run_waypoint(solver, oracle, N, r, K, D, B, variant=variant)
+    # d_free output (getFreeConstraints order) is consistent with the coefficients: derivative k of the
+    # polynomial at t=0 of segment v equals u_v[k]
+    h = N // 2
+    for v in range(1, K):
+        for k in range(1, h):
+            fact = float(np.prod(np.arange(1, k + 1)))
+            got = dfree[:, :, (v - 1) * (h - 1) + (k - 1)]
+            want = out[:, v, :, k] * fact
+            assert np.abs(got - want).max() <= 1e-9 * (1.0 + np.abs(want).max())
     assert prob.kernel == m.KERNEL_WAYPOINT
     assert (status == 0).all()
     err = global_rel_err(out, ref)
@@ -54,16 +69,16 @@ def test_waypoint_kernel_matches_oracle(solver, oracle, N, r, K, D, B):
     # reference-order arithmetic itself is further than 1e-10 from the exact answer (1-D fixtures have
     # short segments, T ~ 1 s; r < N/2-1 cancels harder): there the oracle comparison is loose and
     # test_gpu_vs_truth pins the kernel to the exact answer instead.
-    tol = TOL if ((N, r) in ((10, 4), (8, 3)) and D == 3) else 5e-9
+    tol = TOL if ((N, r) in ((10, 4), (8, 3)) and D == 3) else (5e-9 if N < 12 else 1e-7)
     assert err.max() <= tol, f"max global-relative error {err.max():.3e}"
 
 
 def test_generic_kernel_matches_oracle_on_waypoint_mask(solver, oracle):
-    """Same problem routed through the generic kernel by passing the mask explicitly with K too
-    large for the shared-memory path (K=50, the reference's largest test case)."""
+    """Waypoint topology with K too large for the shared-memory sweeps (K = 100, the largest size of the
+    reference's timing program, polynomial_timing_evaluation.cpp:117) -> generic banded kernel."""
     import torch
     import mav_trajectory_generation_b200 as m
-    N, r, K, D, B = 10, 4, 50, 3, 64
+    N, r, K, D, B = 10, 4, 100, 3, 40
     pos, times = oracle.make_waypoint_batch(K, D, B, base_seed=106)
     ref, _ = oracle.solve_waypoint_batch(N, r, pos, times, n_threads=oracle.hardware_threads())
     prob = m.Problem(N, r, K, D)
@@ -137,8 +152,20 @@ def test_generic_kernel_arbitrary_masks(solver, oracle):
         assert (status.cpu().numpy() == 0).all()
         err = global_rel_err(out.cpu().numpy(), ref)
         assert err.max() <= 5e-9, (trial, N, K, D, err.max())
-        scale = np.abs(dfree_ref).max()
-        assert np.abs(dfree.cpu().numpy() - dfree_ref).max() <= 5e-9 * scale
+        # d_free against the oracle is loose (its QR works on the cancellation-prone A^-T Q A^-1; high free
+        # derivatives are poorly determined in that arithmetic) and tight against the 60-digit solve.
+        got_free = dfree.cpu().numpy()
+        rel = np.abs(got_free - dfree_ref).max() / np.abs(dfree_ref).max()
+        assert rel <= 1e-5, (trial, N, K, D, rel)
+        if trial < 4:
+            import os
+            import sys
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+            import truth
+            tru, tru_free = truth.solve(N, h - 1, mask, values[0], times[0])
+            e_c = np.abs(out.cpu().numpy()[0] - tru).max() / np.abs(tru).max()
+            e_f = np.abs(got_free[0] - tru_free).max() / np.abs(tru_free).max()
+            assert e_c <= 1e-11 and e_f <= 1e-10, (trial, N, K, D, e_c, e_f)
 
 
 def test_waypoint_nonzero_end_derivatives_and_dfree(solver, oracle):

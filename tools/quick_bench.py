@@ -29,27 +29,30 @@ def main():
     dev = torch.device("cuda:0")
     s = m.Solver(0)
     cfgs = [("C3", 10, 4, 16, 3, 262144), ("C2", 10, 4, 8, 3, 65536), ("C4", 8, 3, 4, 3, 1048576)]
-    if len(sys.argv) > 1:
-        cfgs = [c for c in cfgs if c[0] in sys.argv[1:]]
-    for name, N, r, K, D, B in cfgs:
-        prob = m.Problem(N, r, K, D)
-        times, dfix = synth(N, K, D, B, dev)
-        out = torch.empty((B, K, D, N), device=dev, dtype=torch.float64)
-        for _ in range(3):
-            s.solve_linear(prob, times, dfix, coeffs=out)
-        torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
-        ev[0].record()
-        for i in range(10):
-            s.solve_linear(prob, times, dfix, coeffs=out)
-            ev[i + 1].record()
-        torch.cuda.synchronize()
-        ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(10))
-        med = ms[len(ms) // 2]
-        rate = B / (med * 1e-3)
-        gbs = rate * prob.bytes_per_trajectory / 1e9
-        print(json.dumps(dict(cfg=name, N=N, r=r, K=K, D=D, B=B, ms=med, ms_min=ms[0], traj_per_s=rate, GBs=gbs,
-                              frac_hbm=gbs / 6575.4, finite=bool(torch.isfinite(out).all().item()))))
+    cfgs = [c for c in cfgs if c[0] in sys.argv[1:]] or cfgs
+    variants = [int(a[1:]) for a in sys.argv[1:] if a.startswith("v")] or [0]
+    for variant in variants:
+        s.set_option(m.capi.OPT_WAYPOINT_VARIANT, variant)
+        for name, N, r, K, D, B in cfgs:
+            prob = m.Problem(N, r, K, D)
+            times, dfix = synth(N, K, D, B, dev)
+            out = torch.empty((B, K, D, N), device=dev, dtype=torch.float64)
+            for _ in range(3):
+                s.solve_linear(prob, times, dfix, coeffs=out)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
+            ev[0].record()
+            for i in range(10):
+                s.solve_linear(prob, times, dfix, coeffs=out)
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(10))
+            med = ms[len(ms) // 2]
+            rate = B / (med * 1e-3)
+            gbs = rate * prob.bytes_per_trajectory / 1e9
+            print(json.dumps(dict(variant=variant, cfg=name, K=K, B=B, ms=round(med, 4), traj_per_s=round(rate),
+                                  GBs=round(gbs, 1), frac_hbm=round(gbs / 6575.4, 4),
+                                  finite=bool(torch.isfinite(out).all().item()))))
 
 
 if __name__ == "__main__":
