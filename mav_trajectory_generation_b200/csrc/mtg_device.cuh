@@ -19,28 +19,54 @@
 
 namespace mtg {
 
-// Compile-time tables: element access with a compile-time index folds to an immediate /
-// constant-bank operand of the consuming DFMA (no load instruction).
+// Tables in constant memory.  The specialised kernels index them with compile-time constants
+// (fully unrolled loops), so every entry becomes a constant-bank operand c[3][imm] of the
+// consuming DFMA/DMUL -- no load and no register; the generic kernel indexes them at run time
+// with warp-uniform indices (broadcast).
+#define MTG_DECL_A1INV(N_) __constant__ double c_a1inv_##N_[] = MTG_A1INV_##N_;
+#define MTG_DECL_H1(N_, R_) __constant__ double c_h1_##N_##_##R_[] = MTG_H1_##N_##_##R_;
+MTG_DECL_A1INV(2)
+MTG_DECL_A1INV(4)
+MTG_DECL_A1INV(6)
+MTG_DECL_A1INV(8)
+MTG_DECL_A1INV(10)
+MTG_DECL_A1INV(12)
+MTG_DECL_H1(2, 0)
+MTG_DECL_H1(4, 0)
+MTG_DECL_H1(4, 1)
+MTG_DECL_H1(6, 0)
+MTG_DECL_H1(6, 1)
+MTG_DECL_H1(6, 2)
+MTG_DECL_H1(8, 0)
+MTG_DECL_H1(8, 1)
+MTG_DECL_H1(8, 2)
+MTG_DECL_H1(8, 3)
+MTG_DECL_H1(10, 0)
+MTG_DECL_H1(10, 1)
+MTG_DECL_H1(10, 2)
+MTG_DECL_H1(10, 3)
+MTG_DECL_H1(10, 4)
+MTG_DECL_H1(12, 0)
+MTG_DECL_H1(12, 1)
+MTG_DECL_H1(12, 2)
+MTG_DECL_H1(12, 3)
+MTG_DECL_H1(12, 4)
+MTG_DECL_H1(12, 5)
+
 template <int N>
 struct A1Inv;
 template <int N, int R>
 struct H1;
 
-#define MTG_DEF_A1INV(N_)                                                              \
-  template <>                                                                          \
-  struct A1Inv<N_> {                                                                   \
-    static __host__ __device__ __forceinline__ constexpr double at(int r, int c) {     \
-      constexpr double t[] = MTG_A1INV_##N_;                                           \
-      return t[r * N_ + c];                                                            \
-    }                                                                                  \
+#define MTG_DEF_A1INV(N_)                                                                        \
+  template <>                                                                                    \
+  struct A1Inv<N_> {                                                                             \
+    static __device__ __forceinline__ double at(int r, int c) { return c_a1inv_##N_[r * N_ + c]; } \
   };
-#define MTG_DEF_H1(N_, R_)                                                             \
-  template <>                                                                          \
-  struct H1<N_, R_> {                                                                  \
-    static __host__ __device__ __forceinline__ constexpr double at(int r, int c) {     \
-      constexpr double t[] = MTG_H1_##N_##_##R_;                                       \
-      return t[r * N_ + c];                                                            \
-    }                                                                                  \
+#define MTG_DEF_H1(N_, R_)                                                                             \
+  template <>                                                                                          \
+  struct H1<N_, R_> {                                                                                  \
+    static __device__ __forceinline__ double at(int r, int c) { return c_h1_##N_##_##R_[r * N_ + c]; } \
   };
 
 MTG_DEF_A1INV(2)

@@ -15,36 +15,6 @@
 
 namespace mtg {
 
-// Runtime-indexed copies of the tables in constant memory (uniform index across a warp ->
-// broadcast).
-__constant__ double c_a1inv_2[] = MTG_A1INV_2;
-__constant__ double c_a1inv_4[] = MTG_A1INV_4;
-__constant__ double c_a1inv_6[] = MTG_A1INV_6;
-__constant__ double c_a1inv_8[] = MTG_A1INV_8;
-__constant__ double c_a1inv_10[] = MTG_A1INV_10;
-__constant__ double c_a1inv_12[] = MTG_A1INV_12;
-__constant__ double c_h1_2_0[] = MTG_H1_2_0;
-__constant__ double c_h1_4_0[] = MTG_H1_4_0;
-__constant__ double c_h1_4_1[] = MTG_H1_4_1;
-__constant__ double c_h1_6_0[] = MTG_H1_6_0;
-__constant__ double c_h1_6_1[] = MTG_H1_6_1;
-__constant__ double c_h1_6_2[] = MTG_H1_6_2;
-__constant__ double c_h1_8_0[] = MTG_H1_8_0;
-__constant__ double c_h1_8_1[] = MTG_H1_8_1;
-__constant__ double c_h1_8_2[] = MTG_H1_8_2;
-__constant__ double c_h1_8_3[] = MTG_H1_8_3;
-__constant__ double c_h1_10_0[] = MTG_H1_10_0;
-__constant__ double c_h1_10_1[] = MTG_H1_10_1;
-__constant__ double c_h1_10_2[] = MTG_H1_10_2;
-__constant__ double c_h1_10_3[] = MTG_H1_10_3;
-__constant__ double c_h1_10_4[] = MTG_H1_10_4;
-__constant__ double c_h1_12_0[] = MTG_H1_12_0;
-__constant__ double c_h1_12_1[] = MTG_H1_12_1;
-__constant__ double c_h1_12_2[] = MTG_H1_12_2;
-__constant__ double c_h1_12_3[] = MTG_H1_12_3;
-__constant__ double c_h1_12_4[] = MTG_H1_12_4;
-__constant__ double c_h1_12_5[] = MTG_H1_12_5;
-
 __device__ __forceinline__ const double* a1inv_table(int N) {
   switch (N) {
     case 2: return c_a1inv_2;

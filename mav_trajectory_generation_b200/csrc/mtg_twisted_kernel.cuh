@@ -303,22 +303,20 @@ __global__ void __launch_bounds__(32) twisted_solve_kernel(const WaypointParams 
         for (int j = 0; j < m; ++j) df[d * np + (vo - 1) * m + j] = sgn(j) * u[1 + j][d];
     }
   };
-  // emit own-frame segment j (start derivatives sd at own vertex j, end derivatives ed at j+1)
+  // emit own-frame segment j (start derivatives sd at own vertex j, end derivatives ed at j+1).
+  // For the reversed half the ORIGINAL segment starts at own vertex j+1: start = J ed, end = J sd.
+  // The swap is a select per value (no divergent code path); J is folded into the time powers.
   auto emit = [&](int j, double T, double iT, const double (&sd)[h][D], const double (&ed)[h][D]) {
     double* __restrict__ o = out + (long long)seg(j) * D * N;
-    if (half) {  // original orientation: start = J * own end, end = J * own start
-      double s2[h][D], e2[h][D];
+    double s2[h][D], e2[h][D];
 #pragma unroll
-      for (int k = 0; k < h; ++k)
+    for (int k = 0; k < h; ++k)
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          s2[k][d] = (k & 1) ? -ed[k][d] : ed[k][d];
-          e2[k][d] = (k & 1) ? -sd[k][d] : sd[k][d];
-        }
-      emit_segment<N, D>(T, iT, s2, e2, o, valid);
-    } else {
-      emit_segment<N, D>(T, iT, sd, ed, o, valid);
-    }
+      for (int d = 0; d < D; ++d) {
+        s2[k][d] = half ? ed[k][d] : sd[k][d];
+        e2[k][d] = half ? sd[k][d] : ed[k][d];
+      }
+    emit_segment<N, D>(T, iT, s2, e2, o, valid, half != 0);
   };
 
   double ed[h][D];
@@ -330,9 +328,24 @@ __global__ void __launch_bounds__(32) twisted_solve_kernel(const WaypointParams 
   }
   if (half == 0) store_free(nh + 1, ed);
 
+  // prefetched inputs of the next outward step: time of own segment v, position of own vertex v
+  double Tb = __ldg(tt + seg(nh));  // nh == 0: segment 0, used by the final emission
+  double xb[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) xb[d] = __ldg(fx + d * nf + pidx(nh));
+
   for (int v = nmax; v >= 1; --v) {
     if (v <= nh) {
-      const double T = __ldg(tt + seg(v));
+      const double T = Tb;
+      double xv[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) xv[d] = xb[d];
+      Tb = __ldg(tt + seg(v - 1));
+      {
+        const int pn = pidx(v - 1);
+#pragma unroll
+        for (int d = 0; d < D; ++d) xb[d] = __ldg(fx + d * nf + pn);
+      }
       const double iT = fast_rcp(T);
       double L[m][m], inv[m], rhs[m][D];
       {
@@ -379,7 +392,7 @@ __global__ void __launch_bounds__(32) twisted_solve_kernel(const WaypointParams 
           for (int k = j + 1; k < m; ++k) s = fma(-L[k][j], sd[1 + k][d], s);
           sd[1 + j][d] = s * inv[j];
         }
-        sd[0][d] = __ldg(fx + d * nf + pidx(v));
+        sd[0][d] = xv[d];
       }
       store_free(v, sd);
       emit(v, T, iT, sd, ed);
@@ -390,13 +403,13 @@ __global__ void __launch_bounds__(32) twisted_solve_kernel(const WaypointParams 
     }
   }
   {
-    const double T = __ldg(tt + seg(0));
+    const double T = Tb;
     const double iT = fast_rcp(T);
     const int e0 = half ? h + K : 1;
     double sd[h][D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      sd[0][d] = __ldg(fx + d * nf + pidx(0));
+      sd[0][d] = xb[d];
 #pragma unroll
       for (int b = 0; b < m; ++b) sd[1 + b][d] = sgn(b) * __ldg(fx + d * nf + e0 + b);
     }

@@ -79,16 +79,19 @@ __device__ __forceinline__ void segment_powers(double T, double invT, double (&p
 //   sd[k][d], ed[k][d]: derivative k (0..m) at the segment start / end.
 // p_j = T^-j * sum_s A1inv[j][s] * T^(s mod h) * d_s ; for j < h this is d_j / j! exactly as the
 // reference computes it (A^-1 is diagonal there, linear_impl.h:173).
+// `flip`: the derivative values are given in the time-reversed sign convention (derivative k carries
+// (-1)^k); the sign is folded into the time powers (and the 1/k! factors) instead of the data.
 template <int N, int D>
 __device__ __forceinline__ void emit_segment(double T, double invT, const double (&sd)[N / 2][D],
                                              const double (&ed)[N / 2][D], double* __restrict__ out,
-                                             bool valid) {
+                                             bool valid, bool flip = false) {
   constexpr int h = N / 2;
-  double tp[h];     // T^k
+  double tp[h];     // T^k (times (-1)^k when flip)
   double itp[h];    // T^-(h+j)
+  const double Ts = flip ? -T : T;
   tp[0] = 1.0;
 #pragma unroll
-  for (int k = 1; k < h; ++k) tp[k] = tp[k - 1] * T;
+  for (int k = 1; k < h; ++k) tp[k] = tp[k - 1] * Ts;
   itp[0] = pow_int<h>(invT);
 #pragma unroll
   for (int j = 1; j < h; ++j) itp[j] = itp[j - 1] * invT;
@@ -98,7 +101,7 @@ __device__ __forceinline__ void emit_segment(double T, double invT, const double
     double ss[h], se[h];
 #pragma unroll
     for (int k = 0; k < h; ++k) {
-      c[k] = sd[k][d] * A1Inv<N>::at(k, k);
+      c[k] = sd[k][d] * ((flip && (k & 1)) ? -A1Inv<N>::at(k, k) : A1Inv<N>::at(k, k));
       ss[k] = tp[k] * sd[k][d];
       se[k] = tp[k] * ed[k][d];
     }

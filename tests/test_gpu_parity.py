@@ -151,13 +151,13 @@ def test_generic_kernel_arbitrary_masks(solver, oracle):
         torch.cuda.synchronize()
         assert (status.cpu().numpy() == 0).all()
         err = global_rel_err(out.cpu().numpy(), ref)
-        assert err.max() <= 5e-9, (trial, N, K, D, err.max())
+        assert err.max() <= (5e-9 if N <= 10 else 1e-6), (trial, N, K, D, err.max())  # N=12: oracle's own rounding
         # d_free against the oracle is loose (its QR works on the cancellation-prone A^-T Q A^-1; high free
         # derivatives are poorly determined in that arithmetic) and tight against the 60-digit solve.
         got_free = dfree.cpu().numpy()
         rel = np.abs(got_free - dfree_ref).max() / np.abs(dfree_ref).max()
         assert rel <= 1e-5, (trial, N, K, D, rel)
-        if trial < 4:
+        if trial < 4 or N == 12:
             import os
             import sys
             sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
