@@ -95,7 +95,8 @@ int mtg_device_is_sm100(const mtg_handle* h);
 
 /* tuning knobs (results are identical to rounding; used by tests and profiles)
  *   MTG_OPT_WAYPOINT_VARIANT: 0 = default (two lanes per trajectory, twisted factorisation),
- *                             1 = one thread per trajectory, 2 = twisted. */
+ *                             1 = one thread per trajectory, 2 = twisted (state in shared memory),
+ *                             3 = twisted with the sweep state in tensor memory + staged stores. */
 #define MTG_OPT_WAYPOINT_VARIANT 1
 int mtg_set_option(mtg_handle* h, int key, int value);
 

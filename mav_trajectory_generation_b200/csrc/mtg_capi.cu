@@ -13,6 +13,7 @@
 #include "../../include/mtg_b200.h"
 #include "mtg_generic_kernel.cuh"
 #include "mtg_twisted_kernel.cuh"
+#include "mtg_twisted_tmem_kernel.cuh"
 #include "mtg_waypoint_kernel.cuh"
 
 namespace {
@@ -130,11 +131,14 @@ struct WaypointEntry {
   int N, R, D, slots;
   WaypointKernel fn;          // one thread per trajectory
   WaypointKernel fn_twisted;  // two lanes per trajectory (twisted factorisation)
+  void (*fn_tmem)(const mtg::WaypointParams, const mtg::TmemLaunch);  // + state in TMEM, staged output
+  int stage_bytes_per_warp;
 };
 #define MTG_WP(N_, R_, D_)                                                                   \
   {                                                                                          \
     N_, R_, D_, mtg::waypoint_state_slots<N_, D_>(), mtg::waypoint_solve_kernel<N_, R_, D_>, \
-        mtg::twisted_solve_kernel<N_, R_, D_>                                                \
+        mtg::twisted_solve_kernel<N_, R_, D_>, mtg::twisted_tmem_kernel<N_, R_, D_>,         \
+        mtg::tmem_stage_bytes_per_warp<N_, D_>()                                             \
   }
 const WaypointEntry kWaypointKernels[] = {
     MTG_WP(10, 4, 3), MTG_WP(10, 4, 1), MTG_WP(10, 3, 3), MTG_WP(10, 2, 3),
@@ -225,7 +229,48 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
     prm.status = status;
     const size_t smem_v1 = size_t(p->K - 1) * e->slots * 32 * sizeof(double);
     const bool use_v1 = h->waypoint_variant == 1 && smem_v1 <= h->smem_optin;
-    if (use_v1) {
+    if (h->waypoint_variant == 3) {
+      // Pick the TMEM column count / spill split that maximises resident CTAs per SM.
+      cudaFuncAttributes attr;
+      MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)e->fn_tmem));
+      const int nmax = (p->K + 1) / 2 - 1;
+      const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
+      int best_ctas = 0, best_cols = 0, best_ntm = 0;
+      size_t best_smem = 0;
+      const int col_options[] = {512, 256, 128, 64, 32, 0};
+      for (int cols : col_options) {
+        const int ntm = cols ? std::min(nmax, cols / (2 * e->slots)) : 0;
+        if (cols && ntm == 0) continue;
+        const size_t smem = 16 + size_t(4) * e->stage_bytes_per_warp +
+                            size_t(nmax - ntm) * e->slots * mtg::kTmemThreads * sizeof(double);
+        if (smem > h->smem_optin) continue;
+        int ctas = std::min<int>(by_regs, int((228 * 1024) / (smem + 1024)));
+        ctas = std::min(ctas, 16);
+        if (cols) ctas = std::min(ctas, 512 / cols);
+        if (ctas > best_ctas || (ctas == best_ctas && smem < best_smem)) {
+          best_ctas = ctas;
+          best_cols = cols;
+          best_ntm = ntm;
+          best_smem = smem;
+        }
+      }
+      if (best_ctas == 0) {  // sweep state too large for TMEM + shared memory of a 128-thread CTA
+        const size_t smem = size_t(nmax) * e->slots * 32 * sizeof(double);
+        MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn_twisted, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        e->fn_twisted<<<(unsigned)((B + 15) / 16), 32, smem, stream>>>(prm);
+        MTG_CUDA(h, cudaGetLastError());
+        h->launches++;
+        return MTG_OK;
+      }
+      mtg::TmemLaunch tl;
+      tl.n_tmem_blocks = best_ntm;
+      tl.tmem_cols = best_cols;
+      MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)best_smem));
+      const int64_t blocks = (B + 63) / 64;
+      e->fn_tmem<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl);
+    } else if (use_v1) {
       MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v1));
       const int64_t blocks = (B + 31) / 32;
       e->fn<<<(unsigned)blocks, 32, smem_v1, stream>>>(prm);
@@ -360,7 +405,7 @@ int mtg_device_is_sm100(const mtg_handle* h) { return h && h->cc_major == 10; }
 
 int mtg_set_option(mtg_handle* h, int key, int value) {
   if (!h) return MTG_ERR_BAD_ARG;
-  if (key == MTG_OPT_WAYPOINT_VARIANT && value >= 0 && value <= 2) {
+  if (key == MTG_OPT_WAYPOINT_VARIANT && value >= 0 && value <= 3) {
     h->waypoint_variant = value;
     return MTG_OK;
   }

@@ -1,0 +1,652 @@
+// mtg_twisted_tmem_kernel.cuh -- K1 (v3): twisted two-lanes-per-trajectory sweep with the
+// per-thread sweep state held in TENSOR MEMORY and coalesced output.
+//
+// Why TMEM: the sweep state (L_v, inverse pivots, y_v per eliminated vertex; 22 doubles per
+// vertex for N=10, D=3) is what bounds the number of trajectories in flight per SM.  Shared
+// memory alone gives 5 warps/SM at K = 16.  Blackwell's 256 KB tensor memory is otherwise idle
+// on this (tensor-core-free) path, and tcgen05.st / tcgen05.ld with the 32x32b shape give every
+// thread of a warp a private, dynamically indexed row of 512 32-bit columns -- exactly a
+// per-thread LIFO.  A 128-thread CTA covers the 128 TMEM lanes; two CTAs per SM take 256 columns
+// each (128 doubles per thread); what does not fit spills to shared memory [vertex][slot][thread].
+//
+// Output: each lane writes the N coefficients of one (segment, dimension) to a per-warp staging
+// tile with 128-bit stores (row stride N*8 bytes: conflict free), then the warp streams the tile
+// out with 128-bit global stores in which consecutive lanes write consecutive 16-byte pieces
+// (runs of N*8 contiguous bytes) instead of 32 scattered 16-byte stores.
+//
+// Mathematics, frames and index maps: see mtg_twisted_kernel.cuh.
+#pragma once
+
+#include "mtg_twisted_kernel.cuh"
+
+namespace mtg {
+namespace tmem {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 32 bit, repeated along columns: thread i of the warp owns lane (quarter base + i) and
+// moves NV consecutive 32-bit columns starting at taddr.
+template <int NV>
+__device__ __forceinline__ void st(uint32_t taddr, const uint32_t* v);
+template <int NV>
+__device__ __forceinline__ void ld(uint32_t taddr, uint32_t* v);
+
+template <>
+__device__ __forceinline__ void st<2>(uint32_t a, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(a), "r"(v[0]), "r"(v[1]) : "memory");
+}
+template <>
+__device__ __forceinline__ void st<4>(uint32_t a, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void st<8>(uint32_t a, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(a), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void st<16>(uint32_t a, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16};" ::"r"(a),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void ld<2>(uint32_t a, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(a) : "memory");
+}
+template <>
+__device__ __forceinline__ void ld<4>(uint32_t a, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(a)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void ld<8>(uint32_t a, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(a)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void ld<16>(uint32_t a, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(a)
+      : "memory");
+}
+
+// NW 32-bit words starting at column `col` of this thread's lane, greedy chunks of 16/8/4/2.
+template <int NW, int OFF = 0>
+__device__ __forceinline__ void st_words(uint32_t taddr, const uint32_t* w) {
+  if constexpr (NW - OFF >= 16) {
+    st<16>(taddr + OFF, w + OFF);
+    st_words<NW, OFF + 16>(taddr, w);
+  } else if constexpr (NW - OFF >= 8) {
+    st<8>(taddr + OFF, w + OFF);
+    st_words<NW, OFF + 8>(taddr, w);
+  } else if constexpr (NW - OFF >= 4) {
+    st<4>(taddr + OFF, w + OFF);
+    st_words<NW, OFF + 4>(taddr, w);
+  } else if constexpr (NW - OFF >= 2) {
+    st<2>(taddr + OFF, w + OFF);
+    st_words<NW, OFF + 2>(taddr, w);
+  }
+}
+template <int NW, int OFF = 0>
+__device__ __forceinline__ void ld_words(uint32_t taddr, uint32_t* w) {
+  if constexpr (NW - OFF >= 16) {
+    ld<16>(taddr + OFF, w + OFF);
+    ld_words<NW, OFF + 16>(taddr, w);
+  } else if constexpr (NW - OFF >= 8) {
+    ld<8>(taddr + OFF, w + OFF);
+    ld_words<NW, OFF + 8>(taddr, w);
+  } else if constexpr (NW - OFF >= 4) {
+    ld<4>(taddr + OFF, w + OFF);
+    ld_words<NW, OFF + 4>(taddr, w);
+  } else if constexpr (NW - OFF >= 2) {
+    ld<2>(taddr + OFF, w + OFF);
+    ld_words<NW, OFF + 2>(taddr, w);
+  }
+}
+
+}  // namespace tmem
+
+struct TmemLaunch {
+  int n_tmem_blocks;   // eliminated vertices whose state lives in TMEM (the rest spill to shared memory)
+  int tmem_cols;       // power of two >= 32, 0 = no TMEM used
+};
+
+constexpr int kTmemThreads = 128;
+
+template <int N, int D>
+__host__ __device__ constexpr int tmem_stage_bytes_per_warp() {
+  return 32 * (N / 2) * 16;  // one (segment, dimension) row of N doubles per lane
+}
+
+template <int N, int R, int D>
+__global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const WaypointParams prm, const TmemLaunch tl) {
+  constexpr int h = N / 2;
+  constexpr int m = h - 1;
+  constexpr int kL = m * (m + 1) / 2;
+  constexpr int kSlots = kL + m * D;
+  constexpr int kWords = 2 * kSlots;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int kWarps = kTmemThreads / 32;
+  using G = H1<N, R>;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int half = lane & 1;
+  const int K = prm.K;
+  const int nf = prm.n_fixed;
+  const int M = (K + 1) >> 1;
+  const int nh = half ? K - M - 1 : M - 1;
+  const int nmax = M - 1;
+
+  // ---- shared memory carve-up: [holder 16 B][staging: kWarps tiles][spilled state]
+  uint32_t* holder = reinterpret_cast<uint32_t*>(smem_raw);
+  double2* stage = reinterpret_cast<double2*>(smem_raw + 16) + size_t(warp) * 32 * h;
+  double* spill = reinterpret_cast<double*>(smem_raw + 16 + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>()) +
+                  threadIdx.x;
+  auto SP = [&](int blk, int slot) -> double& { return spill[(size_t(blk) * kSlots + slot) * kTmemThreads]; };
+
+  // ---- tensor memory for the sweep state
+  uint32_t tbase = 0;
+  if (tl.tmem_cols > 0) {
+    if (warp == 0) tmem::alloc(tmem::smem_u32(holder), (uint32_t)tl.tmem_cols);
+    tmem::fence_before_sync();
+    __syncthreads();
+    tmem::fence_after_sync();
+    tbase = *holder + (uint32_t(warp * 32) << 16);  // this warp's lane quarter
+  }
+  const int ntm = tl.n_tmem_blocks;
+  auto put_state = [&](int blk, const double (&sv)[kSlots]) {
+    if (blk < ntm) {  // warp-uniform
+      uint32_t w[kWords];
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) {
+        w[2 * i] = (uint32_t)__double2loint(sv[i]);
+        w[2 * i + 1] = (uint32_t)__double2hiint(sv[i]);
+      }
+      tmem::st_words<kWords>(tbase + uint32_t(blk * kWords), w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) SP(blk - ntm, i) = sv[i];
+    }
+  };
+  auto get_state = [&](int blk, double (&sv)[kSlots]) {
+    if (blk < ntm) {
+      uint32_t w[kWords];
+      tmem::ld_words<kWords>(tbase + uint32_t(blk * kWords), w);
+      tmem::wait_ld();
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) sv[i] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) sv[i] = SP(blk - ntm, i);
+    }
+  };
+
+  const long long traj0 = ((long long)blockIdx.x * kWarps + warp) * 16;  // first trajectory of this warp
+  long long traj = traj0 + (lane >> 1);
+  const bool valid = traj < prm.B;
+  if (!valid) traj = prm.B - 1;
+
+  const double* __restrict__ tt = prm.times + traj * K;
+  const double* __restrict__ fx = prm.dfix + traj * (long long)D * nf;
+  auto seg = [&](int j) -> int { return half ? K - 1 - j : j; };
+  auto pidx = [&](int v) -> int {
+    const int o = half ? K - v : v;
+    return o == 0 ? 0 : (o < K ? h + o - 1 : h + K - 1);
+  };
+  auto sgn = [&](int idx) -> double { return (half && !(idx & 1)) ? -1.0 : 1.0; };
+
+  // ---- per-lane constants of the cooperative store: piece e = it*32 + lane of the staging tile is
+  // 16 bytes c2 of row r (row r = lane r of this warp = trajectory r>>1, half r&1).
+  int st_off[h];      // double2 offset relative to the warp's first trajectory (segment/dimension added later)
+  int st_nh[h];       // eliminated-vertex count of the row's half (row active in step v iff v <= st_nh)
+  bool st_half[h], st_ok[h];
+#pragma unroll
+  for (int it = 0; it < h; ++it) {
+    const int e = it * 32 + lane;
+    const int r = e / h, c2 = e - r * h;
+    st_off[it] = (r >> 1) * (K * D * h) + c2;
+    st_half[it] = (r & 1) != 0;
+    st_nh[it] = (r & 1) ? K - M - 1 : M - 1;
+    st_ok[it] = traj0 + (r >> 1) < prm.B;
+  }
+  double2* __restrict__ out2 =
+      reinterpret_cast<double2*>(prm.coeffs) + (traj0 < prm.B ? traj0 : 0) * (long long)K * D * h;
+
+  // emit own-frame segment j for every lane of the warp at once (convergent).  `act`: this lane's
+  // values are meaningful; rows of inactive lanes are not stored.  v_step: the sweep step (0 = final).
+  auto emit_all = [&](int j, int v_step, double T, double iT, const double (&sd)[h][D], const double (&ed)[h][D]) {
+    // original orientation: start = J*(own end) for the reversed half; J folded into the powers
+    double tp[h], itp[h];
+    const double Ts = half ? -T : T;
+    tp[0] = 1.0;
+#pragma unroll
+    for (int k = 1; k < h; ++k) tp[k] = tp[k - 1] * Ts;
+    itp[0] = pow_int<h>(iT);
+#pragma unroll
+    for (int k = 1; k < h; ++k) itp[k] = itp[k - 1] * iT;
+    const int segF = j * (D * h), segB = (K - 1 - j) * (D * h);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double c[N], ss[h], se[h];
+#pragma unroll
+      for (int k = 0; k < h; ++k) {
+        const double s0 = half ? ed[k][d] : sd[k][d];
+        const double e0 = half ? sd[k][d] : ed[k][d];
+        c[k] = s0 * ((half && (k & 1)) ? -A1Inv<N>::at(k, k) : A1Inv<N>::at(k, k));
+        ss[k] = tp[k] * s0;
+        se[k] = tp[k] * e0;
+      }
+#pragma unroll
+      for (int q = 0; q < h; ++q) {
+        double acc = A1Inv<N>::at(h + q, 0) * ss[0];
+#pragma unroll
+        for (int k = 1; k < h; ++k) acc = fma(A1Inv<N>::at(h + q, k), ss[k], acc);
+#pragma unroll
+        for (int k = 0; k < h; ++k) acc = fma(A1Inv<N>::at(h + q, h + k), se[k], acc);
+        c[h + q] = acc * itp[q];
+      }
+#pragma unroll
+      for (int q = 0; q < h; ++q) stage[lane * h + q] = make_double2(c[2 * q], c[2 * q + 1]);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < h; ++it) {
+        const double2 val = stage[it * 32 + lane];
+        if (st_ok[it] && v_step <= st_nh[it]) out2[st_off[it] + (st_half[it] ? segB : segF) + d * h] = val;
+      }
+      __syncwarp();
+    }
+  };
+
+  int stat = 0;
+  double Wp[m][m], yp[m][D], Cee[m][m], cps[m], cpe[m], bcar[m][D], xm[D], xc[D];
+  double Tn, xnn[D];
+  {
+    const double T0 = __ldg(tt + seg(0));
+    if (!(T0 > 0.0)) stat |= kStatusBadTime;
+    const double iT0 = fast_rcp(T0);
+    double pw[N - 1];
+    segment_powers<N, R>(T0, iT0, pw);
+    const int e0 = half ? h + K : 1;
+#pragma unroll
+    for (int a = 0; a < m; ++a) {
+#pragma unroll
+      for (int b = 0; b < m; ++b) {
+        Cee[a][b] = pw[a + b + 2] * G::at(h + 1 + a, h + 1 + b);
+        Wp[a][b] = 0.0;
+      }
+      cps[a] = pw[a + 1] * G::at(h + 1 + a, 0);
+      cpe[a] = pw[a + 1] * G::at(h + 1 + a, h);
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double u0[m];
+#pragma unroll
+      for (int b = 0; b < m; ++b) u0[b] = sgn(b) * __ldg(fx + d * nf + e0 + b);
+#pragma unroll
+      for (int a = 0; a < m; ++a) {
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < m; ++b) acc = fma(pw[a + b + 2] * G::at(h + 1 + a, 1 + b), u0[b], acc);
+        bcar[a][d] = -acc;
+        yp[a][d] = 0.0;
+      }
+      xm[d] = __ldg(fx + d * nf + pidx(0));
+      xc[d] = __ldg(fx + d * nf + pidx(1));
+    }
+    Tn = __ldg(tt + seg(1));
+    const int p2 = pidx(2);
+#pragma unroll
+    for (int d = 0; d < D; ++d) xnn[d] = __ldg(fx + d * nf + p2);
+  }
+
+  // ---------------------------------------------------------------- sweep towards the middle
+  for (int v = 1; v <= nmax; ++v) {
+    double sv[kSlots];
+#pragma unroll
+    for (int i = 0; i < kSlots; ++i) sv[i] = 0.0;
+    if (v <= nh) {
+      const double T = Tn;
+      double xn[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) xn[d] = xnn[d];
+      {
+        const int jn = v + 1 < K ? v + 1 : K - 1;
+        const int vn = v + 2 <= K ? v + 2 : K;
+        Tn = __ldg(tt + seg(jn));
+        const int pn = pidx(vn);
+#pragma unroll
+        for (int d = 0; d < D; ++d) xnn[d] = __ldg(fx + d * nf + pn);
+      }
+      if (!(T > 0.0)) stat |= kStatusBadTime;
+      const double iT = fast_rcp(T);
+      double pw[N - 1];
+      segment_powers<N, R>(T, iT, pw);
+
+      double Dp[m][m], E[m][m], bb[m][D];
+#pragma unroll
+      for (int a = 0; a < m; ++a) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          double s = fma(pw[a + b + 2], G::at(1 + a, 1 + b), Cee[a][b]);
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = fma(-Wp[k][a], Wp[k][b], s);
+          Dp[a][b] = s;
+        }
+#pragma unroll
+        for (int b = 0; b < m; ++b) E[a][b] = pw[a + b + 2] * G::at(1 + a, h + 1 + b);
+        const double gmid = fma(pw[a + 1], G::at(1 + a, 0), cpe[a]);
+        const double gnext = pw[a + 1] * G::at(1 + a, h);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          double s = bcar[a][d];
+          s = fma(-cps[a], xm[d], s);
+          s = fma(-gmid, xc[d], s);
+          s = fma(-gnext, xn[d], s);
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = fma(-Wp[k][a], yp[k][d], s);
+          bb[a][d] = s;
+        }
+      }
+      double L[m][m], inv[m];
+#pragma unroll
+      for (int j = 0; j < m; ++j) {
+        double s = Dp[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
+        if (!(s > 0.0)) stat |= kStatusNotSpd;
+        inv[j] = fast_rsqrt(s);
+#pragma unroll
+        for (int i = j + 1; i < m; ++i) {
+          double t = Dp[i][j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) t = fma(-L[i][k], L[j][k], t);
+          L[i][j] = t * inv[j];
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+          double s = bb[j][d];
+#pragma unroll
+          for (int k = 0; k < j; ++k) s = fma(-L[j][k], yp[k][d], s);
+          yp[j][d] = s * inv[j];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < m; ++c) {
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+          double s = E[j][c];
+#pragma unroll
+          for (int k = 0; k < j; ++k) s = fma(-L[j][k], Wp[k][c], s);
+          Wp[j][c] = s * inv[j];
+        }
+      }
+      {
+        int slot = 0;
+#pragma unroll
+        for (int i = 1; i < m; ++i)
+#pragma unroll
+          for (int j = 0; j < i; ++j) sv[slot++] = L[i][j];
+#pragma unroll
+        for (int j = 0; j < m; ++j) sv[slot++] = inv[j];
+#pragma unroll
+        for (int j = 0; j < m; ++j)
+#pragma unroll
+          for (int d = 0; d < D; ++d) sv[slot++] = yp[j][d];
+      }
+#pragma unroll
+      for (int a = 0; a < m; ++a) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b) Cee[a][b] = pw[a + b + 2] * G::at(h + 1 + a, h + 1 + b);
+        cps[a] = pw[a + 1] * G::at(h + 1 + a, 0);
+        cpe[a] = pw[a + 1] * G::at(h + 1 + a, h);
+#pragma unroll
+        for (int d = 0; d < D; ++d) bcar[a][d] = 0.0;
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        xm[d] = xc[d];
+        xc[d] = xn[d];
+      }
+    }
+    __syncwarp();
+    put_state(v - 1, sv);  // all lanes (tcgen05.st is warp-collective)
+  }
+  __syncwarp();
+  if (ntm > 0) tmem::wait_st();
+
+  // ---------------------------------------------------------------- middle vertex
+  double um[m][D];
+  {
+    double Dl[m][m], bl[m][D];
+#pragma unroll
+    for (int a = 0; a < m; ++a) {
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        double s = Cee[a][b];
+#pragma unroll
+        for (int k = 0; k < m; ++k) s = fma(-Wp[k][a], Wp[k][b], s);
+        Dl[a][b] = s;
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        double s = bcar[a][d];
+        s = fma(-cps[a], xm[d], s);
+        s = fma(-cpe[a], xc[d], s);
+#pragma unroll
+        for (int k = 0; k < m; ++k) s = fma(-Wp[k][a], yp[k][d], s);
+        bl[a][d] = s;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < m; ++a) {
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        const double o = __shfl_xor_sync(kFull, Dl[a][b], 1);
+        Dl[a][b] += ((a + b) & 1) ? -o : o;
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double o = __shfl_xor_sync(kFull, bl[a][d], 1);
+        bl[a][d] += (a & 1) ? o : -o;
+      }
+    }
+    stat |= __shfl_xor_sync(kFull, stat, 1);
+    double L[m][m], inv[m];
+#pragma unroll
+    for (int j = 0; j < m; ++j) {
+      double s = Dl[j][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
+      if (!(s > 0.0)) stat |= kStatusNotSpd;
+      inv[j] = fast_rsqrt(s);
+#pragma unroll
+      for (int i = j + 1; i < m; ++i) {
+        double t = Dl[i][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) t = fma(-L[i][k], L[j][k], t);
+        L[i][j] = t * inv[j];
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double y[m];
+#pragma unroll
+      for (int j = 0; j < m; ++j) {
+        double s = bl[j][d];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L[j][k], y[k], s);
+        y[j] = s * inv[j];
+      }
+#pragma unroll
+      for (int j = m - 1; j >= 0; --j) {
+        double s = y[j];
+#pragma unroll
+        for (int k = j + 1; k < m; ++k) s = fma(-L[k][j], um[k][d], s);
+        um[j][d] = s * inv[j];
+      }
+    }
+  }
+  if (valid && half == 0 && prm.status != nullptr) prm.status[traj] = stat;
+
+  // ---------------------------------------------------------------- outward back-substitution
+  const int np = (K - 1) * m;
+  double* __restrict__ df = prm.dfree != nullptr ? prm.dfree + traj * (long long)D * np : nullptr;
+  auto store_free = [&](int v_own, const double (&u)[h][D]) {
+    if (df != nullptr && valid) {
+      const int vo = half ? K - v_own : v_own;
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int j = 0; j < m; ++j) df[d * np + (vo - 1) * m + j] = sgn(j) * u[1 + j][d];
+    }
+  };
+
+  double ed[h][D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    ed[0][d] = xc[d];
+#pragma unroll
+    for (int j = 0; j < m; ++j) ed[1 + j][d] = um[j][d];
+  }
+  if (half == 0) store_free(nh + 1, ed);
+
+  double Tb = __ldg(tt + seg(nh));
+  double xb[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) xb[d] = __ldg(fx + d * nf + pidx(nh));
+
+  for (int v = nmax; v >= 1; --v) {
+    double sv[kSlots];
+    get_state(v - 1, sv);  // all lanes
+    const bool act = v <= nh;
+    double T = 1.0, iT = 1.0;
+    double sd[h][D];
+#pragma unroll
+    for (int k = 0; k < h; ++k)
+#pragma unroll
+      for (int d = 0; d < D; ++d) sd[k][d] = 0.0;
+    if (act) {
+      T = Tb;
+      double xv[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) xv[d] = xb[d];
+      Tb = __ldg(tt + seg(v - 1));
+      {
+        const int pn = pidx(v - 1);
+#pragma unroll
+        for (int d = 0; d < D; ++d) xb[d] = __ldg(fx + d * nf + pn);
+      }
+      iT = fast_rcp(T);
+      double L[m][m], inv[m], rhs[m][D];
+      {
+        int slot = 0;
+#pragma unroll
+        for (int i = 1; i < m; ++i)
+#pragma unroll
+          for (int j = 0; j < i; ++j) L[i][j] = sv[slot++];
+#pragma unroll
+        for (int j = 0; j < m; ++j) inv[j] = sv[slot++];
+#pragma unroll
+        for (int j = 0; j < m; ++j)
+#pragma unroll
+          for (int d = 0; d < D; ++d) rhs[j][d] = sv[slot++];
+      }
+      double pw[N - 1];
+      segment_powers<N, R>(T, iT, pw);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        double t[m];
+#pragma unroll
+        for (int a = 0; a < m; ++a) {
+          double s = 0.0;
+#pragma unroll
+          for (int b = 0; b < m; ++b) s = fma(pw[a + b + 2] * G::at(1 + a, h + 1 + b), ed[1 + b][d], s);
+          t[a] = s;
+        }
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+          double s = t[j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) s = fma(-L[j][k], t[k], s);
+          t[j] = s * inv[j];
+          rhs[j][d] -= t[j];
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+#pragma unroll
+        for (int j = m - 1; j >= 0; --j) {
+          double s = rhs[j][d];
+#pragma unroll
+          for (int k = j + 1; k < m; ++k) s = fma(-L[k][j], sd[1 + k][d], s);
+          sd[1 + j][d] = s * inv[j];
+        }
+        sd[0][d] = xv[d];
+      }
+      store_free(v, sd);
+    }
+    __syncwarp();
+    emit_all(v, v, T, iT, sd, ed);
+    if (act) {
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int k = 0; k < h; ++k) ed[k][d] = sd[k][d];
+    }
+  }
+  {
+    const double T = Tb;
+    const double iT = fast_rcp(T);
+    const int e0 = half ? h + K : 1;
+    double sd[h][D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      sd[0][d] = xb[d];
+#pragma unroll
+      for (int b = 0; b < m; ++b) sd[1 + b][d] = sgn(b) * __ldg(fx + d * nf + e0 + b);
+    }
+    __syncwarp();
+    emit_all(0, 0, T, iT, sd, ed);
+  }
+
+  if (tl.tmem_cols > 0) {
+    tmem::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem::dealloc(*holder, (uint32_t)tl.tmem_cols);
+  }
+}
+
+}  // namespace mtg

@@ -37,7 +37,7 @@ def run_waypoint(solver, oracle, N, r, K, D, B, base_seed=1000, want_free=True, 
     return prob, pos, times, ref, out.cpu().numpy(), status.cpu().numpy(), (dfree.cpu().numpy() if want_free else None)
 
 
-@pytest.mark.parametrize("variant", [1, 2])  # 1: thread per trajectory, 2: twisted (two lanes per trajectory)
+@pytest.mark.parametrize("variant", [1, 2, 3])  # 1: thread per trajectory, 2: twisted, 3: twisted + TMEM state
 @pytest.mark.parametrize("N,r,K,D,B", [
     (10, 4, 16, 3, 2048),   # C3 headline shape
     (10, 4, 8, 3, 2048),    # C2
