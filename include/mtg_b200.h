@@ -94,7 +94,7 @@ int64_t mtg_launch_count(const mtg_handle* h);
 int mtg_device_is_sm100(const mtg_handle* h);
 
 /* tuning knobs (results are identical to rounding; used by tests and profiles)
- *   MTG_OPT_WAYPOINT_VARIANT: 0 = default (two lanes per trajectory, twisted factorisation),
+ *   MTG_OPT_WAYPOINT_VARIANT: 0 = default (= 3, falling back to 2 when the state does not fit),
  *                             1 = one thread per trajectory, 2 = twisted (state in shared memory),
  *                             3 = twisted with the sweep state in tensor memory + staged stores. */
 #define MTG_OPT_WAYPOINT_VARIANT 1

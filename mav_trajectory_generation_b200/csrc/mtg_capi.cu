@@ -229,7 +229,7 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
     prm.status = status;
     const size_t smem_v1 = size_t(p->K - 1) * e->slots * 32 * sizeof(double);
     const bool use_v1 = h->waypoint_variant == 1 && smem_v1 <= h->smem_optin;
-    if (h->waypoint_variant == 3) {
+    if (h->waypoint_variant == 0 || h->waypoint_variant == 3) {
       // Pick the TMEM column count / spill split that maximises resident CTAs per SM.
       cudaFuncAttributes attr;
       MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)e->fn_tmem));

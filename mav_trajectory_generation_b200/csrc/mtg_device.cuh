@@ -58,15 +58,41 @@ struct A1Inv;
 template <int N, int R>
 struct H1;
 
-#define MTG_DEF_A1INV(N_)                                                                        \
-  template <>                                                                                    \
-  struct A1Inv<N_> {                                                                             \
+// Two ways to feed a table entry with a compile-time index to an FP64 instruction (sm_100 DFMA/DMUL
+// take register or uniform-register operands, not c[bank][offset]):
+//   A1Inv / H1        entries are loaded from constant memory (LDC/LDCU) and the compiler keeps the hot
+//                     ones in registers across loop iterations: fewest instructions, ~50 more live
+//                     registers.  Used by the kernels that are not register-bound.
+//   A1InvImm / H1Imm  entries become 64-bit immediates moved into uniform registers right before use
+//                     (2 UMOV per use, zero live registers).  Used by the TMEM kernel, which runs at the
+//                     255-register limit (2 CTAs x 128 threads per SM) and must not spill.
+template <int N>
+struct A1InvImm;
+template <int N, int R>
+struct H1Imm;
+#define MTG_DEF_A1INV(N_)                                                                          \
+  template <>                                                                                      \
+  struct A1Inv<N_> {                                                                               \
     static __device__ __forceinline__ double at(int r, int c) { return c_a1inv_##N_[r * N_ + c]; } \
+  };                                                                                               \
+  template <>                                                                                      \
+  struct A1InvImm<N_> {                                                                            \
+    static __device__ __forceinline__ constexpr double at(int r, int c) {                          \
+      constexpr double t[] = MTG_A1INV_##N_;                                                       \
+      return t[r * N_ + c];                                                                        \
+    }                                                                                              \
   };
 #define MTG_DEF_H1(N_, R_)                                                                             \
   template <>                                                                                          \
   struct H1<N_, R_> {                                                                                  \
     static __device__ __forceinline__ double at(int r, int c) { return c_h1_##N_##_##R_[r * N_ + c]; } \
+  };                                                                                                   \
+  template <>                                                                                          \
+  struct H1Imm<N_, R_> {                                                                               \
+    static __device__ __forceinline__ constexpr double at(int r, int c) {                              \
+      constexpr double t[] = MTG_H1_##N_##_##R_;                                                       \
+      return t[r * N_ + c];                                                                            \
+    }                                                                                                  \
   };
 
 MTG_DEF_A1INV(2)

@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
   constexpr int kWords = 2 * kSlots;
   constexpr unsigned kFull = 0xffffffffu;
   constexpr int kWarps = kTmemThreads / 32;
-  using G = H1<N, R>;
+  using G = H1Imm<N, R>;     // immediates: this kernel is register-bound (see mtg_device.cuh)
+  using AI = A1InvImm<N>;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -262,17 +263,17 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
       for (int k = 0; k < h; ++k) {
         const double s0 = half ? ed[k][d] : sd[k][d];
         const double e0 = half ? sd[k][d] : ed[k][d];
-        c[k] = s0 * ((half && (k & 1)) ? -A1Inv<N>::at(k, k) : A1Inv<N>::at(k, k));
+        c[k] = s0 * ((half && (k & 1)) ? -AI::at(k, k) : AI::at(k, k));
         ss[k] = tp[k] * s0;
         se[k] = tp[k] * e0;
       }
 #pragma unroll
       for (int q = 0; q < h; ++q) {
-        double acc = A1Inv<N>::at(h + q, 0) * ss[0];
+        double acc = AI::at(h + q, 0) * ss[0];
 #pragma unroll
-        for (int k = 1; k < h; ++k) acc = fma(A1Inv<N>::at(h + q, k), ss[k], acc);
+        for (int k = 1; k < h; ++k) acc = fma(AI::at(h + q, k), ss[k], acc);
 #pragma unroll
-        for (int k = 0; k < h; ++k) acc = fma(A1Inv<N>::at(h + q, h + k), se[k], acc);
+        for (int k = 0; k < h; ++k) acc = fma(AI::at(h + q, h + k), se[k], acc);
         c[h + q] = acc * itp[q];
       }
 #pragma unroll
