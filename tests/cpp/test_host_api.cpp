@@ -165,6 +165,45 @@ static void testTwoVerticesSetup() {
   EXPECT(opt.getNumberFreeConstraints() == 0 && opt.getNumberFixedConstraints() == 10);
 }
 
+// BASELINE config C1: the README example (reference README.md:105-139), v_max = a_max = 2.
+static void testReadmeExample() {
+  const int dimension = 3, derivative_to_optimize = derivative_order::SNAP;
+  Vertex::Vector vertices;
+  Vertex start(dimension), middle(dimension), end(dimension);
+  start.makeStartOrEnd(Eigen::Vector3d(0, 0, 1), derivative_to_optimize);
+  vertices.push_back(start);
+  middle.addConstraint(derivative_order::POSITION, Eigen::Vector3d(1, 2, 3));
+  vertices.push_back(middle);
+  end.makeStartOrEnd(Eigen::Vector3d(2, 1, 5), derivative_to_optimize);
+  vertices.push_back(end);
+  std::vector<double> segment_times = estimateSegmentTimes(vertices, 2.0, 2.0);
+  PolynomialOptimization<10> opt(dimension);
+  opt.setupFromVertices(vertices, segment_times, derivative_to_optimize);
+  EXPECT(opt.solveLinear());
+  EXPECT(opt.getNumberFixedConstraints() == 11 && opt.getNumberFreeConstraints() == 4);
+  Segment::Vector segments;
+  opt.getSegments(&segments);
+  checkPath(vertices, segments);
+  // x-coefficients of both segments (reproduced by the CPU oracle, tests/test_oracle.py)
+  const double s0[10] = {0, 0, 0, 0, 0, 1.339252819683e-02, -7.845546057916e-03, 1.954568943734e-03,
+                         -2.392908039981e-04, 1.181394415329e-05};
+  const double s1[10] = {1, 5.845294839088e-01, 3.552673810634e-03, -4.357594222295e-02, -1.385817588887e-03,
+                         7.025146441719e-03, -4.564409065003e-03, 1.688225883678e-03, -2.991260062373e-04,
+                         1.981495243341e-05};
+  const Eigen::VectorXd c0 = segments[0][0].getCoefficients(), c1 = segments[1][0].getCoefficients();
+  for (int i = 0; i < 10; ++i) {
+    EXPECT_NEAR(c0[i], s0[i], 2e-13);
+    EXPECT_NEAR(c1[i], s1[i], 2e-12);
+  }
+  Trajectory trajectory;
+  opt.getTrajectory(&trajectory);
+  EXPECT_NEAR(trajectory.getMaxTime(), segment_times[0] + segment_times[1], 1e-12);
+  const Eigen::VectorXd mid = trajectory.evaluate(segment_times[0], derivative_order::POSITION);
+  EXPECT_NEAR(mid[0], 1.0, 1e-9);
+  EXPECT_NEAR(mid[1], 2.0, 1e-9);
+  EXPECT_NEAR(mid[2], 3.0, 1e-9);
+}
+
 // UnconstrainedLinearEstimateSegmentTimes (test :271-306)
 static void testUnconstrainedLinear(const Params& p) {
   Vertex::Vector vertices = fixtureVertices(p);
@@ -273,6 +312,7 @@ int main(int argc, char** argv) {
   testLayoutOnly();
   if (!cpu_only) {
     testTwoVerticesSetup();
+    testReadmeExample();
     for (const Params& p : kParams) testUnconstrainedLinear(p);
     for (const Params& p : kParams) testConstraintPacking(p);
     testBatchMatchesSingle();
