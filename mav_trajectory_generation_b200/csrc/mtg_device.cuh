@@ -63,9 +63,12 @@ struct H1;
 //   A1Inv / H1        entries are loaded from constant memory (LDC/LDCU) and the compiler keeps the hot
 //                     ones in registers across loop iterations: fewest instructions, ~50 more live
 //                     registers.  Used by the kernels that are not register-bound.
-//   A1InvImm / H1Imm  entries become 64-bit immediates moved into uniform registers right before use
-//                     (2 UMOV per use, zero live registers).  Used by the TMEM kernel, which runs at the
-//                     255-register limit (2 CTAs x 128 threads per SM) and must not spill.
+//   A1InvImm / H1Imm  entries are compile-time immediates (zero live registers).  H1Imm is the INTEGER-
+//                     SCALED table H(1;r) * lcm(denominators) (the reduced system's solution is invariant
+//                     to scaling H): its entries are exact small integers whose odd part fits 21 bits, so
+//                     they are encoded in the 32-bit immediate field of DFMA/DMUL -- no UMOV, no register,
+//                     no load.  A(1)^-1 entries are small dyadic rationals and are immediates as they are.
+//                     Used by the TMEM kernel, which runs at the register limit (2 CTAs x 128 threads/SM).
 template <int N>
 struct A1InvImm;
 template <int N, int R>
@@ -88,9 +91,9 @@ struct H1Imm;
     static __device__ __forceinline__ double at(int r, int c) { return c_h1_##N_##_##R_[r * N_ + c]; } \
   };                                                                                                   \
   template <>                                                                                          \
-  struct H1Imm<N_, R_> {                                                                               \
+  struct H1Imm<N_, R_> { /* integer-scaled table: exact, entries fit the FP64 immediate field */       \
     static __device__ __forceinline__ constexpr double at(int r, int c) {                              \
-      constexpr double t[] = MTG_H1_##N_##_##R_;                                                       \
+      constexpr double t[] = MTG_H1S_##N_##_##R_;                                                      \
       return t[r * N_ + c];                                                                            \
     }                                                                                                  \
   };

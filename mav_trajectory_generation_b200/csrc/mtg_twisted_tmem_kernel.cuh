@@ -146,6 +146,16 @@ __host__ __device__ constexpr int tmem_stage_bytes_per_warp() {
   return 32 * (N / 2) * 16;  // one (segment, dimension) row of N doubles per lane
 }
 
+template <int D>
+__host__ __device__ constexpr int tmem_prefetch_bytes() {
+  return 2 * (1 + D) * kTmemThreads * 8;
+}
+
+__device__ __forceinline__ void cp_async8(const double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tmem::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int N, int R, int D>
 __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const WaypointParams prm, const TmemLaunch tl) {
   constexpr int h = N / 2;
@@ -171,7 +181,13 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
   // ---- shared memory carve-up: [holder 16 B][staging: kWarps tiles][spilled state]
   uint32_t* holder = reinterpret_cast<uint32_t*>(smem_raw);
   double2* stage = reinterpret_cast<double2*>(smem_raw + 16) + size_t(warp) * 32 * h;
-  double* spill = reinterpret_cast<double*>(smem_raw + 16 + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>()) +
+  // per-thread prefetch ring for the next step's inputs (segment time + D positions), filled by
+  // cp.async: a register prefetch would share its scoreboard slot with the load being consumed and the
+  // consumer would wait for the NEW loads as well (measured: 25 % of all stall samples).
+  double* pf = reinterpret_cast<double*>(smem_raw + 16 + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>()) + threadIdx.x;
+  auto PF = [&](int buf, int slot) -> double* { return pf + (size_t(buf) * (1 + D) + slot) * kTmemThreads; };
+  double* spill = reinterpret_cast<double*>(smem_raw + 16 + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>() +
+                                            tmem_prefetch_bytes<D>()) +
                   threadIdx.x;
   auto SP = [&](int blk, int slot) -> double& { return spill[(size_t(blk) * kSlots + slot) * kTmemThreads]; };
 
@@ -225,6 +241,13 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
     return o == 0 ? 0 : (o < K ? h + o - 1 : h + K - 1);
   };
   auto sgn = [&](int idx) -> double { return (half && !(idx & 1)) ? -1.0 : 1.0; };
+  // prefetch (time of own segment j, position of own vertex v) into ring buffer `buf`
+  auto pf_issue = [&](int buf, int j, int v) {
+    cp_async8(PF(buf, 0), tt + seg(j));
+    const int pn = pidx(v);
+#pragma unroll
+    for (int d = 0; d < D; ++d) cp_async8(PF(buf, 1 + d), fx + d * nf + pn);
+  };
 
   // ---- per-lane constants of the cooperative store: piece e = it*32 + lane of the staging tile is
   // 16 bytes c2 of row r (row r = lane r of this warp = trajectory r>>1, half r&1).
@@ -290,7 +313,6 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
 
   int stat = 0;
   double Wp[m][m], yp[m][D], Cee[m][m], cps[m], cpe[m], bcar[m][D], xm[D], xc[D];
-  double Tn, xnn[D];
   {
     const double T0 = __ldg(tt + seg(0));
     if (!(T0 > 0.0)) stat |= kStatusBadTime;
@@ -324,10 +346,7 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
       xm[d] = __ldg(fx + d * nf + pidx(0));
       xc[d] = __ldg(fx + d * nf + pidx(1));
     }
-    Tn = __ldg(tt + seg(1));
-    const int p2 = pidx(2);
-#pragma unroll
-    for (int d = 0; d < D; ++d) xnn[d] = __ldg(fx + d * nf + p2);
+    pf_issue(1, 1, 2);  // inputs of sweep step v = 1 -> ring buffer (v & 1)
   }
 
   // ---------------------------------------------------------------- sweep towards the middle
@@ -336,17 +355,15 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
 #pragma unroll
     for (int i = 0; i < kSlots; ++i) sv[i] = 0.0;
     if (v <= nh) {
-      const double T = Tn;
+      cp_async_wait_all();
+      const double T = *PF(v & 1, 0);
       double xn[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) xn[d] = xnn[d];
-      {
+      for (int d = 0; d < D; ++d) xn[d] = *PF(v & 1, 1 + d);
+      {  // prefetch the next step's inputs (clamped indices: never out of bounds)
         const int jn = v + 1 < K ? v + 1 : K - 1;
         const int vn = v + 2 <= K ? v + 2 : K;
-        Tn = __ldg(tt + seg(jn));
-        const int pn = pidx(vn);
-#pragma unroll
-        for (int d = 0; d < D; ++d) xnn[d] = __ldg(fx + d * nf + pn);
+        pf_issue((v + 1) & 1, jn, vn);
       }
       if (!(T > 0.0)) stat |= kStatusBadTime;
       const double iT = fast_rcp(T);
@@ -544,10 +561,7 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
   }
   if (half == 0) store_free(nh + 1, ed);
 
-  double Tb = __ldg(tt + seg(nh));
-  double xb[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) xb[d] = __ldg(fx + d * nf + pidx(nh));
+  pf_issue(nh & 1, nh, nh);  // inputs of the first outward step (or of the final emission when nh == 0)
 
   for (int v = nmax; v >= 1; --v) {
     double sv[kSlots];
@@ -560,16 +574,12 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
 #pragma unroll
       for (int d = 0; d < D; ++d) sd[k][d] = 0.0;
     if (act) {
-      T = Tb;
+      cp_async_wait_all();
+      T = *PF(v & 1, 0);
       double xv[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) xv[d] = xb[d];
-      Tb = __ldg(tt + seg(v - 1));
-      {
-        const int pn = pidx(v - 1);
-#pragma unroll
-        for (int d = 0; d < D; ++d) xb[d] = __ldg(fx + d * nf + pn);
-      }
+      for (int d = 0; d < D; ++d) xv[d] = *PF(v & 1, 1 + d);
+      pf_issue((v - 1) & 1, v - 1, v - 1);
       iT = fast_rcp(T);
       double L[m][m], inv[m], rhs[m][D];
       {
@@ -629,13 +639,14 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
     }
   }
   {
-    const double T = Tb;
+    cp_async_wait_all();
+    const double T = *PF(0, 0);
     const double iT = fast_rcp(T);
     const int e0 = half ? h + K : 1;
     double sd[h][D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      sd[0][d] = xb[d];
+      sd[0][d] = *PF(0, 1 + d);
 #pragma unroll
       for (int b = 0; b < m; ++b) sd[1 + b][d] = sgn(b) * __ldg(fx + d * nf + e0 + b);
     }
