@@ -203,13 +203,13 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
   const int ntm = tl.n_tmem_blocks;
   auto put_state = [&](int blk, const double (&sv)[kSlots]) {
     if (blk < ntm) {  // warp-uniform
-      uint32_t w[kWords];
+      // one tcgen05.st.x2 per double: a double already is an aligned register pair, so no packing
+      // moves are needed (a wide .x16 store wants 16 consecutive registers)
 #pragma unroll
       for (int i = 0; i < kSlots; ++i) {
-        w[2 * i] = (uint32_t)__double2loint(sv[i]);
-        w[2 * i + 1] = (uint32_t)__double2hiint(sv[i]);
+        const uint32_t w[2] = {(uint32_t)__double2loint(sv[i]), (uint32_t)__double2hiint(sv[i])};
+        tmem::st<2>(tbase + uint32_t(blk * kWords + 2 * i), w);
       }
-      tmem::st_words<kWords>(tbase + uint32_t(blk * kWords), w);
     } else {
 #pragma unroll
       for (int i = 0; i < kSlots; ++i) SP(blk - ntm, i) = sv[i];
@@ -351,9 +351,7 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
 
   // ---------------------------------------------------------------- sweep towards the middle
   for (int v = 1; v <= nmax; ++v) {
-    double sv[kSlots];
-#pragma unroll
-    for (int i = 0; i < kSlots; ++i) sv[i] = 0.0;
+    double sv[kSlots];  // lanes with v > nh store whatever is here; they never read it back
     if (v <= nh) {
       cp_async_wait_all();
       const double T = *PF(v & 1, 0);
@@ -568,11 +566,7 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
     get_state(v - 1, sv);  // all lanes
     const bool act = v <= nh;
     double T = 1.0, iT = 1.0;
-    double sd[h][D];
-#pragma unroll
-    for (int k = 0; k < h; ++k)
-#pragma unroll
-      for (int d = 0; d < D; ++d) sd[k][d] = 0.0;
+    double sd[h][D];  // inactive lanes (odd K only) emit garbage rows that are never stored
     if (act) {
       cp_async_wait_all();
       T = *PF(v & 1, 0);
