@@ -69,56 +69,65 @@ def ncu_traffic(cfg):
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    """Samples SM clock and throttle reasons DURING the timed region.  The region is tens of milliseconds,
+    far shorter than nvidia-smi's sampling period, so NVML is polled from a thread (nvidia_ml_py); falls
+    back to one nvidia-smi query if NVML is unavailable."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+               ("hw_thermal_slowdown", 0x40), ("hw_power_brake", 0x80))
 
     def __init__(self, index=0):
-        self.samples = []
-        self.proc = None
         self.index = index
+        self.samples = []
+        self.reason_bits = 0
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        self._handle = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) >= 6:
-                self.samples.append(parts)
+    def _poll(self):
+        p = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(p.nvmlDeviceGetClockInfo(self._handle, p.NVML_CLOCK_SM)))
+                self.reason_bits |= int(p.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
+            except Exception:
+                try:
+                    self.reason_bits |= int(p.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+                except Exception:
+                    pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
+        if self._nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            sm = sorted(self.samples)
+            reasons = [name for name, bit in self.REASONS if self.reason_bits & bit]
+            if sm:
+                return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                        "samples": len(sm), "source": "nvml"}
+        try:  # fallback: a single nvidia-smi query right after the region
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index),
+                                  "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            a, b, c = [x.strip() for x in out.strip().split(",")[:3]]
+            return {"sm_mhz": float(a), "sm_max_mhz": float(b), "reasons": [c], "samples": 1, "source": "nvidia-smi"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for p in self.samples:
-            try:
-                sm.append(float(p[0]))
-                mx.append(float(p[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
 
 
 def synth_batch(torch, N, K, D, B, device, seed):
@@ -164,9 +173,14 @@ def cpu_baseline_sample(N, r, K, D, target_seconds=12.0, max_traj=2000000):
     n = int(min(max_traj, max(4096, rate * target_seconds)))
     pos, times = O.make_waypoint_batch(K, D, n, base_seed=1000)
     _, s = O.solve_waypoint_batch(N, r, pos, times, n_threads=threads, mode=0, want_coeffs=False)
+    # the nonlinear optimiser's inner step only (updateSegmentTimes + solveLinear on a set-up object,
+    # reference polynomial_optimization_nonlinear_impl.h:569-570): max over threads of the clocked time
+    n1 = min(n, 200000)
+    _, s1 = O.solve_waypoint_batch(N, r, pos[:n1], times[:n1], n_threads=threads, mode=1, want_coeffs=False)
     return {"value": n / s, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n} trajectories of the workload (mt19937 fixture seeds 1000+b), construct+setupFromVertices+"
-                      f"solveLinear per trajectory, {threads} host threads, {s:.2f} s wall"}, n, s
+                      f"solveLinear per trajectory, {threads} host threads, {s:.2f} s wall",
+            "update_times_plus_solve_only": n1 / s1}, n, s
 
 
 def run_reference(args):

@@ -39,7 +39,7 @@ def run_waypoint(solver, oracle, N, r, K, D, B, base_seed=1000, want_free=True, 
 
 @pytest.mark.parametrize("variant", [1, 2, 3])  # 1: thread per trajectory, 2: twisted, 3: twisted + TMEM state
 @pytest.mark.parametrize("N,r,K,D,B", [
-    (10, 4, 16, 3, 2048),   # C3 headline shape
+    (10, 4, 16, 3, 4096),   # C3 headline shape, >= 4096 bit-exact fixture trajectories
     (10, 4, 8, 3, 2048),    # C2
     (8, 3, 4, 3, 4096),     # C4
     (10, 4, 2, 3, 257),     # C1 shape, ragged batch: only the middle vertex
