@@ -140,9 +140,18 @@ struct WaypointEntry {
         mtg::twisted_solve_kernel<N_, R_, D_>, mtg::twisted_tmem_kernel<N_, R_, D_>,         \
         mtg::tmem_stage_bytes_per_warp<N_, D_>()                                             \
   }
+// v1 (thread per trajectory) is kept for the headline shapes only (cross-check / profiles)
+#define MTG_WP2(N_, R_, D_)                                                                           \
+  {                                                                                                   \
+    N_, R_, D_, mtg::waypoint_state_slots<N_, D_>(), nullptr, mtg::twisted_solve_kernel<N_, R_, D_>,  \
+        mtg::twisted_tmem_kernel<N_, R_, D_>, mtg::tmem_stage_bytes_per_warp<N_, D_>()                \
+  }
 const WaypointEntry kWaypointKernels[] = {
-    MTG_WP(10, 4, 3), MTG_WP(10, 4, 1), MTG_WP(10, 3, 3), MTG_WP(10, 2, 3),
-    MTG_WP(8, 3, 3),  MTG_WP(8, 3, 1),  MTG_WP(12, 5, 3),
+    MTG_WP(10, 4, 3),  MTG_WP(10, 4, 1),  MTG_WP2(10, 4, 2), MTG_WP2(10, 4, 4),   // min snap, N = 10
+    MTG_WP(10, 3, 3),  MTG_WP2(10, 3, 1), MTG_WP(10, 2, 3),  MTG_WP2(10, 2, 1),   // jerk / acceleration on N = 10
+    MTG_WP(8, 3, 3),   MTG_WP(8, 3, 1),   MTG_WP2(8, 3, 2),  MTG_WP2(8, 3, 4),    // min jerk, N = 8
+    MTG_WP(12, 5, 3),  MTG_WP2(12, 5, 1), MTG_WP2(12, 5, 4),                      // N = 12 (feasibility tests)
+    MTG_WP2(6, 2, 3),  MTG_WP2(6, 2, 1),                                          // min acceleration, N = 6
 };
 
 const WaypointEntry* find_waypoint(const mtg_handle* h, const mtg_problem* p, const Layout& L) {
@@ -228,7 +237,7 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
     prm.dfree = dfree;
     prm.status = status;
     const size_t smem_v1 = size_t(p->K - 1) * e->slots * 32 * sizeof(double);
-    const bool use_v1 = h->waypoint_variant == 1 && smem_v1 <= h->smem_optin;
+    const bool use_v1 = h->waypoint_variant == 1 && e->fn != nullptr && smem_v1 <= h->smem_optin;
     if (h->waypoint_variant == 0 || h->waypoint_variant == 3) {
       // Pick the TMEM column count / spill split that maximises resident CTAs per SM.
       cudaFuncAttributes attr;

@@ -49,6 +49,11 @@ def run_waypoint(solver, oracle, N, r, K, D, B, base_seed=1000, want_free=True, 
     (10, 4, 16, 1, 300),
     (10, 3, 5, 3, 300),
     (12, 5, 6, 3, 300),
+    (10, 4, 6, 2, 200),     # D = 2 / 4 specialisations
+    (10, 4, 7, 4, 200),
+    (8, 3, 6, 2, 150),
+    (6, 2, 5, 3, 200),      # N = 6 min acceleration
+    (12, 5, 4, 4, 100),
 ])
 def test_waypoint_kernel_matches_oracle(solver, oracle, N, r, K, D, B, variant):
     import mav_trajectory_generation_b200 as m
