@@ -376,6 +376,24 @@ def run_ours(args):
     e2e_value = world * B * e2e_steps / t_e2e
     e2e_ok = bool((h_status == 0).all().item()) and bool(torch.allclose(h_coeffs.to(dev), coeffs, rtol=0, atol=0))
 
+    # ---------------- "next" row 8f-1: fused Nfabian time allocation + packing (positions in)
+    fused_value = None
+    try:
+        pos_d = synth_batch(torch, N, K, D, B, dev, seed=1234 + rank)[0].contiguous()
+        for _ in range(3):
+            solver.solve_waypoints_nfabian(N, r, pos_d, 3.0, 5.0, 6.5, coeffs=coeffs)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nf_steps = max(1, min(args.steps, 20))
+        f0.record()
+        for _ in range(nf_steps):
+            solver.solve_waypoints_nfabian(N, r, pos_d, 3.0, 5.0, 6.5, coeffs=coeffs)
+        f1.record()
+        torch.cuda.synchronize()
+        fused_value = B * nf_steps / (f0.elapsed_time(f1) * 1e-3)
+    except Exception as e:  # optional extra, never fails the bench
+        fused_value = f"failed: {e}"
+
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -399,6 +417,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(8 * B * K * D * N + 4 * B), "steps": e2e_steps,
                     "bitwise_equal_to_device_path": e2e_ok},
             "gpu_launches": int(launches), "clocks": clocks, "results_ok": ok,
+            "fused_waypoint_entry_traj_per_s_rank0": fused_value,
             "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -113,6 +113,16 @@ int mtg_solve_linear_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, c
                                const double* d_fixed, double* coeffs, double* d_free, int32_t* status,
                                void* stream);
 
+/* SURVEY.md 8f-1 ("next" row): time allocation + constraint packing fused into the solve, for the
+ * createRandomVertices topology.  positions [B][K+1][D]; segment times are computed on the device as
+ * estimateSegmentTimesNfabian(v_max, a_max, magic) (reference src/vertex.cpp:255-272; pass magic = 6.5
+ * for the reference default), start/end derivatives 1..N/2-1 are zero (Vertex::makeStartOrEnd,
+ * src/vertex.cpp:147-153).  coeffs [B][K][D][N]; seg_times_out [B][K] and status are optional.
+ * Reads 8*(K+1)*D bytes per trajectory instead of 8*(K + D*n_fixed). */
+int mtg_solve_waypoints_nfabian_batch_f64(mtg_handle* h, int32_t N, int32_t r, int32_t K, int32_t D, int64_t B,
+                                          const double* positions, double v_max, double a_max, double magic,
+                                          double* coeffs, double* seg_times_out, int32_t* status, void* stream);
+
 /* updateSegmentsFromCompactConstraints for given d_free (setFreeConstraints path). */
 int mtg_coeffs_from_constraints_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B,
                                           const double* seg_times, const double* d_fixed,

@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
     "mtg_coeffs_from_constraints_batch_host_f64", "mtg_compute_cost_batch_host_f64",
     "mtg_host_alloc", "mtg_host_free", "mtg_device_alloc", "mtg_device_free", "mtg_memcpy_h2d",
     "mtg_memcpy_d2h", "mtg_stream_synchronize", "mtg_version", "mtg_set_option",
+    "mtg_solve_waypoints_nfabian_batch_f64",
 ]
 
 
@@ -76,6 +77,8 @@ def load():
     L.mtg_stream_synchronize.argtypes = [vp, vp]
     L.mtg_version.restype = C.c_int
     L.mtg_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.mtg_solve_waypoints_nfabian_batch_f64.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i64, dp,
+                                                        C.c_double, C.c_double, C.c_double, dp, dp, dp, vp]
     for name in EXPORTED_SYMBOLS:
         getattr(L, name)  # AttributeError if the library does not export what the header declares
     _lib = L
@@ -157,6 +160,23 @@ class Solver:
             d_free.data_ptr() if d_free is not None else None,
             status.data_ptr() if status is not None else None, s)
         self._check(rc, "mtg_solve_linear_batch_f64")
+        return coeffs
+
+    def solve_waypoints_nfabian(self, N, r, positions, v_max, a_max, magic=6.5, coeffs=None, seg_times_out=None,
+                                status=None, stream=None):
+        """positions: CUDA float64 [B][K+1][D] -> coeffs [B][K][D][N] (fused Nfabian times + packing)."""
+        import torch
+        B, K1, D = positions.shape
+        K = K1 - 1
+        assert positions.is_cuda and positions.dtype == torch.float64 and positions.is_contiguous()
+        if coeffs is None:
+            coeffs = torch.empty((B, K, D, N), dtype=torch.float64, device=positions.device)
+        s = stream if stream is not None else torch.cuda.current_stream(positions.device).cuda_stream
+        rc = self.lib.mtg_solve_waypoints_nfabian_batch_f64(
+            self.h, N, r, K, D, B, positions.data_ptr(), float(v_max), float(a_max), float(magic), coeffs.data_ptr(),
+            seg_times_out.data_ptr() if seg_times_out is not None else None,
+            status.data_ptr() if status is not None else None, s)
+        self._check(rc, "mtg_solve_waypoints_nfabian_batch_f64")
         return coeffs
 
     def coeffs_from_constraints(self, prob, seg_times, d_fixed, d_free, coeffs=None, stream=None):

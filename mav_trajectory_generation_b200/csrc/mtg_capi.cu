@@ -46,6 +46,8 @@ struct mtg_handle {
   std::vector<CachedTopology> topologies;
   double* scratch = nullptr;
   size_t scratch_bytes = 0;
+  double* pack_scratch = nullptr;  // times + d_fixed produced by nfabian_pack_kernel
+  size_t pack_scratch_bytes = 0;
   // host-pointer pipeline
   static constexpr int kPipe = 3;
   cudaStream_t streams[kPipe] = {nullptr, nullptr, nullptr};
@@ -133,18 +135,20 @@ struct WaypointEntry {
   WaypointKernel fn_twisted;  // two lanes per trajectory (twisted factorisation)
   void (*fn_tmem)(const mtg::WaypointParams, const mtg::TmemLaunch);  // + state in TMEM, staged output
   int stage_bytes_per_warp;
+  void (*fn_tmem_fused)(const mtg::WaypointParams, const mtg::TmemLaunch);  // + Nfabian times / packing fused
 };
 #define MTG_WP(N_, R_, D_)                                                                   \
   {                                                                                          \
     N_, R_, D_, mtg::waypoint_state_slots<N_, D_>(), mtg::waypoint_solve_kernel<N_, R_, D_>, \
         mtg::twisted_solve_kernel<N_, R_, D_>, mtg::twisted_tmem_kernel<N_, R_, D_>,         \
-        mtg::tmem_stage_bytes_per_warp<N_, D_>()                                             \
+        mtg::tmem_stage_bytes_per_warp<N_, D_>(), mtg::twisted_tmem_kernel<N_, R_, D_, true> \
   }
 // v1 (thread per trajectory) is kept for the headline shapes only (cross-check / profiles)
 #define MTG_WP2(N_, R_, D_)                                                                           \
   {                                                                                                   \
     N_, R_, D_, mtg::waypoint_state_slots<N_, D_>(), nullptr, mtg::twisted_solve_kernel<N_, R_, D_>,  \
-        mtg::twisted_tmem_kernel<N_, R_, D_>, mtg::tmem_stage_bytes_per_warp<N_, D_>()                \
+        mtg::twisted_tmem_kernel<N_, R_, D_>, mtg::tmem_stage_bytes_per_warp<N_, D_>(),               \
+        mtg::twisted_tmem_kernel<N_, R_, D_, true>                                                    \
   }
 const WaypointEntry kWaypointKernels[] = {
     MTG_WP(10, 4, 3),  MTG_WP(10, 4, 1),  MTG_WP2(10, 4, 2), MTG_WP2(10, 4, 4),   // min snap, N = 10
@@ -219,9 +223,15 @@ struct DeviceGuard {
   }
 };
 
+struct FusedInput {
+  const double* positions;
+  double v_max, a_max, magic;
+  double* times_out;
+};
+
 int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int64_t B, const double* times,
                  const double* dfix, const double* dfree_in, double* coeffs, double* dfree, int32_t* status,
-                 cudaStream_t stream, bool backsub_only) {
+                 cudaStream_t stream, bool backsub_only, const FusedInput* fused = nullptr) {
   const Layout& L = topo->layout;
   if (B == 0) return MTG_OK;
   const int kind = backsub_only ? MTG_KERNEL_NOFREE : route(h, p, L);
@@ -236,9 +246,14 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
     prm.coeffs = coeffs;
     prm.dfree = dfree;
     prm.status = status;
+    prm.positions = fused ? fused->positions : nullptr;
+    prm.v_max = fused ? fused->v_max : 0.0;
+    prm.a_max = fused ? fused->a_max : 0.0;
+    prm.magic = fused ? fused->magic : 0.0;
+    prm.times_out = fused ? fused->times_out : nullptr;
     const size_t smem_v1 = size_t(p->K - 1) * e->slots * 32 * sizeof(double);
     const bool use_v1 = h->waypoint_variant == 1 && e->fn != nullptr && smem_v1 <= h->smem_optin;
-    if (h->waypoint_variant == 0 || h->waypoint_variant == 3) {
+    if (h->waypoint_variant == 0 || h->waypoint_variant == 3 || fused) {
       // Pick the TMEM column count / spill split that maximises resident CTAs per SM.
       cudaFuncAttributes attr;
       MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)e->fn_tmem));
@@ -263,6 +278,7 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
           best_smem = smem;
         }
       }
+      if (best_ctas == 0 && fused) return MTG_ERR_ALLOC;  // caller falls back to pack + solve
       if (best_ctas == 0) {  // sweep state too large for TMEM + shared memory of a 128-thread CTA
         const size_t smem = size_t(nmax) * e->slots * 32 * sizeof(double);
         MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn_twisted, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -278,7 +294,9 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
       MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)best_smem));
       const int64_t blocks = (B + 63) / 64;
-      e->fn_tmem<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl);
+      auto fn = fused ? e->fn_tmem_fused : e->fn_tmem;
+      MTG_CUDA(h, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem));
+      fn<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl);
     } else if (use_v1) {
       MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v1));
       const int64_t blocks = (B + 31) / 32;
@@ -399,6 +417,7 @@ void mtg_destroy(mtg_handle* h) {
   cudaDeviceSynchronize();
   for (auto& t : h->topologies) cudaFree(t.d_slot_col);
   if (h->scratch) cudaFree(h->scratch);
+  if (h->pack_scratch) cudaFree(h->pack_scratch);
   for (int i = 0; i < mtg_handle::kPipe; ++i) {
     if (h->dev_buf[i]) cudaFree(h->dev_buf[i]);
     if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
@@ -450,6 +469,60 @@ int mtg_solve_linear_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, c
   if (!topo) return MTG_ERR_CUDA;
   return launch_solve(h, p, topo, B, seg_times, d_fixed, nullptr, coeffs, d_free, status, (cudaStream_t)stream,
                       false);
+}
+
+int mtg_solve_waypoints_nfabian_batch_f64(mtg_handle* h, int32_t N, int32_t r, int32_t K, int32_t D, int64_t B,
+                                          const double* positions, double v_max, double a_max, double magic,
+                                          double* coeffs, double* seg_times_out, int32_t* status, void* stream) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  mtg_problem p = {N, r, K, D, nullptr};
+  if (!valid_problem(&p) || B < 0 || !(v_max > 0.0) || !(a_max > 0.0) || (B > 0 && (!positions || !coeffs))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  if (B == 0) return MTG_OK;
+  DeviceGuard g(h->device);
+  CachedTopology* topo = get_topology(h, &p);
+  if (!topo) return MTG_ERR_CUDA;
+  const Layout& L = topo->layout;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (route(h, &p, L) == MTG_KERNEL_WAYPOINT) {
+    FusedInput f = {positions, v_max, a_max, magic, seg_times_out};
+    const int rc = launch_solve(h, &p, topo, B, nullptr, nullptr, nullptr, coeffs, nullptr, status, s, false, &f);
+    if (rc != MTG_ERR_ALLOC) return rc;
+  }
+  // no fused specialisation: pack (times, d_fixed) with a small kernel, then the regular path
+  const size_t n_t = size_t(B) * K, n_f = size_t(B) * D * L.n_fixed;
+  if ((n_t + n_f) * 8 > h->pack_scratch_bytes) {
+    if (h->pack_scratch) {
+      MTG_CUDA(h, cudaDeviceSynchronize());
+      cudaFree(h->pack_scratch);
+      h->pack_scratch = nullptr;
+      h->pack_scratch_bytes = 0;
+    }
+    MTG_CUDA(h, cudaMalloc(&h->pack_scratch, (n_t + n_f) * 8));
+    h->pack_scratch_bytes = (n_t + n_f) * 8;
+  }
+  double* t_buf = seg_times_out ? seg_times_out : h->pack_scratch;
+  double* f_buf = h->pack_scratch + n_t;
+  mtg::PackParams pk;
+  pk.N = N;
+  pk.K = K;
+  pk.D = D;
+  pk.n_fixed = L.n_fixed;
+  pk.B = B;
+  pk.positions = positions;
+  pk.v_max = v_max;
+  pk.a_max = a_max;
+  pk.magic = magic;
+  pk.times = t_buf;
+  pk.dfix = f_buf;
+  const int threads = 128;
+  const int64_t blocks = std::min<int64_t>((B + threads - 1) / threads, int64_t(h->sm_count) * 16);
+  mtg::nfabian_pack_kernel<<<(unsigned)blocks, threads, 0, s>>>(pk);
+  MTG_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return launch_solve(h, &p, topo, B, t_buf, f_buf, nullptr, coeffs, nullptr, status, s, false);
 }
 
 int mtg_coeffs_from_constraints_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B,

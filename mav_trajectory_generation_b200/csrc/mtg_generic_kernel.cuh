@@ -207,6 +207,44 @@ __global__ void __launch_bounds__(128) generic_solve_kernel(const GenericParams 
 #undef RHS
 }
 
+// estimateSegmentTimesNfabian (reference src/vertex.cpp:255-272) + the waypoint-topology d_fixed packing
+// (linear_impl.h:233-247) for configurations without a fused specialised kernel.
+struct PackParams {
+  int N, K, D, n_fixed;
+  long long B;
+  const double* __restrict__ positions;  // [B][K+1][D]
+  double v_max, a_max, magic;
+  double* __restrict__ times;            // [B][K]
+  double* __restrict__ dfix;             // [B][D][n_fixed]
+};
+
+__global__ void __launch_bounds__(128) nfabian_pack_kernel(const PackParams prm) {
+  const int K = prm.K, D = prm.D, h = prm.N / 2, nf = prm.n_fixed;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x; traj < prm.B; traj += nthreads) {
+    const double* __restrict__ pos = prm.positions + traj * (long long)(K + 1) * D;
+    double* __restrict__ fx = prm.dfix + traj * (long long)D * nf;
+    for (int d = 0; d < D; ++d) {
+      for (int c = 0; c < nf; ++c) fx[d * nf + c] = 0.0;
+      fx[d * nf] = pos[d];
+      for (int v = 1; v < K; ++v) fx[d * nf + h + v - 1] = pos[v * D + d];
+      fx[d * nf + h + K - 1] = pos[K * D + d];
+    }
+    for (int i = 0; i < K; ++i) {
+      double n2 = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double e = __dsub_rn(pos[(i + 1) * D + d], pos[i * D + d]);
+        n2 = __dadd_rn(n2, __dmul_rn(e, e));
+      }
+      const double distance = sqrt(n2);
+      const double lead = __dmul_rn(__ddiv_rn(distance, prm.v_max), 2.0);
+      const double ex = exp(__dmul_rn(__ddiv_rn(-distance, prm.v_max), 2.0));
+      prm.times[traj * K + i] =
+          __dmul_rn(lead, __dadd_rn(1.0, __dmul_rn(__ddiv_rn(__dmul_rn(prm.magic, prm.v_max), prm.a_max), ex)));
+    }
+  }
+}
+
 // computeCost() (linear_impl.h:123-140): 0.5 * sum c^T Q(T) c with
 // Q[a][b] = 2 B(r,a) B(r,b) T^(a+b-2r+1) / (a+b-2r+1)   (:567-583).
 struct CostParams {

@@ -156,7 +156,7 @@ __device__ __forceinline__ void cp_async8(const double* smem_dst, const double* 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int N, int R, int D>
+template <int N, int R, int D, bool FUSED = false>
 __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const WaypointParams prm, const TmemLaunch tl) {
   constexpr int h = N / 2;
   constexpr int m = h - 1;
@@ -233,21 +233,30 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
   const bool valid = traj < prm.B;
   if (!valid) traj = prm.B - 1;
 
-  const double* __restrict__ tt = prm.times + traj * K;
-  const double* __restrict__ fx = prm.dfix + traj * (long long)D * nf;
+  const double* __restrict__ tt = FUSED ? nullptr : prm.times + traj * K;
+  const double* __restrict__ fx =
+      FUSED ? prm.positions + traj * (long long)(K + 1) * D : prm.dfix + traj * (long long)D * nf;
   auto seg = [&](int j) -> int { return half ? K - 1 - j : j; };
   auto pidx = [&](int v) -> int {
     const int o = half ? K - v : v;
     return o == 0 ? 0 : (o < K ? h + o - 1 : h + K - 1);
   };
   auto sgn = [&](int idx) -> double { return (half && !(idx & 1)) ? -1.0 : 1.0; };
+  // address of coordinate d of own-frame vertex v
+  auto xaddr = [&](int v, int d) -> const double* {
+    if constexpr (FUSED) {
+      return fx + (half ? K - v : v) * D + d;
+    } else {
+      return fx + d * nf + pidx(v);
+    }
+  };
   // prefetch (time of own segment j, position of own vertex v) into ring buffer `buf`
   auto pf_issue = [&](int buf, int j, int v) {
-    cp_async8(PF(buf, 0), tt + seg(j));
-    const int pn = pidx(v);
+    if constexpr (!FUSED) cp_async8(PF(buf, 0), tt + seg(j));
 #pragma unroll
-    for (int d = 0; d < D; ++d) cp_async8(PF(buf, 1 + d), fx + d * nf + pn);
+    for (int d = 0; d < D; ++d) cp_async8(PF(buf, 1 + d), xaddr(v, d));
   };
+  double* __restrict__ tout = (FUSED && prm.times_out != nullptr) ? prm.times_out + traj * K : nullptr;
 
   // ---- per-lane constants of the cooperative store: piece e = it*32 + lane of the staging tile is
   // 16 bytes c2 of row r (row r = lane r of this warp = trajectory r>>1, half r&1).
@@ -314,7 +323,17 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
   int stat = 0;
   double Wp[m][m], yp[m][D], Cee[m][m], cps[m], cpe[m], bcar[m][D], xm[D], xc[D];
   {
-    const double T0 = __ldg(tt + seg(0));
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      xm[d] = __ldg(xaddr(0, d));
+      xc[d] = __ldg(xaddr(1, d));
+    }
+    double T0;
+    if constexpr (FUSED) {
+      T0 = nfabian_time<D>(xm, xc, prm.v_max, prm.a_max, prm.magic);
+    } else {
+      T0 = __ldg(tt + seg(0));
+    }
     if (!(T0 > 0.0)) stat |= kStatusBadTime;
     const double iT0 = fast_rcp(T0);
     double pw[N - 1];
@@ -334,7 +353,7 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
     for (int d = 0; d < D; ++d) {
       double u0[m];
 #pragma unroll
-      for (int b = 0; b < m; ++b) u0[b] = sgn(b) * __ldg(fx + d * nf + e0 + b);
+      for (int b = 0; b < m; ++b) u0[b] = FUSED ? 0.0 : sgn(b) * __ldg(fx + d * nf + e0 + b);
 #pragma unroll
       for (int a = 0; a < m; ++a) {
         double acc = 0.0;
@@ -343,8 +362,6 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
         bcar[a][d] = -acc;
         yp[a][d] = 0.0;
       }
-      xm[d] = __ldg(fx + d * nf + pidx(0));
-      xc[d] = __ldg(fx + d * nf + pidx(1));
     }
     pf_issue(1, 1, 2);  // inputs of sweep step v = 1 -> ring buffer (v & 1)
   }
@@ -354,10 +371,15 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
     double sv[kSlots];  // lanes with v > nh store whatever is here; they never read it back
     if (v <= nh) {
       cp_async_wait_all();
-      const double T = *PF(v & 1, 0);
       double xn[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) xn[d] = *PF(v & 1, 1 + d);
+      double T;
+      if constexpr (FUSED) {
+        T = nfabian_time<D>(xc, xn, prm.v_max, prm.a_max, prm.magic);
+      } else {
+        T = *PF(v & 1, 0);
+      }
       {  // prefetch the next step's inputs (clamped indices: never out of bounds)
         const int jn = v + 1 < K ? v + 1 : K - 1;
         const int vn = v + 2 <= K ? v + 2 : K;
@@ -569,10 +591,18 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
     double sd[h][D];  // inactive lanes (odd K only) emit garbage rows that are never stored
     if (act) {
       cp_async_wait_all();
-      T = *PF(v & 1, 0);
       double xv[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) xv[d] = *PF(v & 1, 1 + d);
+      if constexpr (FUSED) {
+        double xe[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xe[d] = ed[0][d];
+        T = nfabian_time<D>(xv, xe, prm.v_max, prm.a_max, prm.magic);
+        if (tout != nullptr && valid) tout[seg(v)] = T;
+      } else {
+        T = *PF(v & 1, 0);
+      }
       pf_issue((v - 1) & 1, v - 1, v - 1);
       iT = fast_rcp(T);
       double L[m][m], inv[m], rhs[m][D];
@@ -634,16 +664,28 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
   }
   {
     cp_async_wait_all();
-    const double T = *PF(0, 0);
-    const double iT = fast_rcp(T);
     const int e0 = half ? h + K : 1;
     double sd[h][D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       sd[0][d] = *PF(0, 1 + d);
 #pragma unroll
-      for (int b = 0; b < m; ++b) sd[1 + b][d] = sgn(b) * __ldg(fx + d * nf + e0 + b);
+      for (int b = 0; b < m; ++b) sd[1 + b][d] = FUSED ? 0.0 : sgn(b) * __ldg(fx + d * nf + e0 + b);
     }
+    double T;
+    if constexpr (FUSED) {
+      double xs[D], xe[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        xs[d] = sd[0][d];
+        xe[d] = ed[0][d];
+      }
+      T = nfabian_time<D>(xs, xe, prm.v_max, prm.a_max, prm.magic);
+      if (tout != nullptr && valid) tout[seg(0)] = T;
+    } else {
+      T = *PF(0, 0);
+    }
+    const double iT = fast_rcp(T);
     __syncwarp();
     emit_all(0, 0, T, iT, sd, ed);
   }

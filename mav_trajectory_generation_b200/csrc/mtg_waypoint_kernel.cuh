@@ -41,7 +41,32 @@ struct WaypointParams {
   double* __restrict__ coeffs;        // [B][K][D][N]
   double* __restrict__ dfree;         // [B][D][(K-1)*m] or null
   int* __restrict__ status;           // [B] or null
+  // fused time allocation + constraint packing: when `positions` is set the kernels
+  // read waypoints [B][K+1][D] instead of (times, dfix), compute the segment times with
+  // estimateSegmentTimesNfabian (reference src/vertex.cpp:255-272) and use zero start/end derivatives
+  // (Vertex::makeStartOrEnd, src/vertex.cpp:147-153).
+  const double* __restrict__ positions;
+  double v_max, a_max, magic;
+  double* __restrict__ times_out;     // [B][K] or null
 };
+
+// t = distance / v_max * 2 * (1 + magic * v_max / a_max * exp(-distance / v_max * 2)), evaluated in the
+// reference's order with no FMA contraction (the CPU oracle is built with -ffp-contract=off).
+template <int D>
+__device__ __forceinline__ double nfabian_time(const double (&a)[D], const double (&b)[D], double v_max, double a_max,
+                                               double magic) {
+  double n2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double e = __dsub_rn(b[d], a[d]);
+    n2 = __dadd_rn(n2, __dmul_rn(e, e));
+  }
+  const double distance = sqrt(n2);
+  const double lead = __dmul_rn(__ddiv_rn(distance, v_max), 2.0);
+  const double ex = exp(__dmul_rn(__ddiv_rn(-distance, v_max), 2.0));
+  const double fac = __dadd_rn(1.0, __dmul_rn(__ddiv_rn(__dmul_rn(magic, v_max), a_max), ex));
+  return __dmul_rn(lead, fac);
+}
 
 template <int N, int D>
 __host__ __device__ constexpr int waypoint_state_slots() {

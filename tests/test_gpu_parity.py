@@ -327,3 +327,24 @@ def test_full_size_properties_c3(solver):
     a = solver.solve_linear(prob, times[:half].contiguous(), dfix[:half].contiguous())
     b = solver.solve_linear(prob, times[half:].contiguous(), dfix[half:].contiguous())
     assert torch.equal(torch.cat([a, b]), out)
+
+
+@pytest.mark.parametrize("N,r,K,D,B", [(10, 4, 16, 3, 1024), (8, 3, 4, 3, 777), (10, 4, 5, 2, 130), (10, 4, 6, 5, 64),
+                                       (10, 4, 100, 3, 24)])
+def test_fused_nfabian_waypoint_entry(solver, oracle, N, r, K, D, B):
+    """positions in, estimateSegmentTimesNfabian + constraint packing on the device.  The
+    last two cases have no fused specialisation (D = 5: generic kernel; K = 100: state too large) and go
+    through the pack-kernel fallback."""
+    import torch
+    pos, times = oracle.make_waypoint_batch(K, D, B, base_seed=4000)   # v_max 3, a_max 5, magic 6.5
+    ref, _ = oracle.solve_waypoint_batch(N, r, pos, times, n_threads=oracle.hardware_threads())
+    status = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+    t_out = torch.zeros((B, K), dtype=torch.float64, device="cuda")
+    out = solver.solve_waypoints_nfabian(N, r, torch.from_numpy(pos).cuda(), 3.0, 5.0, 6.5, seg_times_out=t_out,
+                                         status=status)
+    torch.cuda.synchronize()
+    assert (status.cpu().numpy() == 0).all()
+    # device exp() vs glibc exp(): at most a couple of ulps apart
+    np.testing.assert_allclose(t_out.cpu().numpy(), times, rtol=4e-16, atol=0)
+    tol = TOL if (N, r) in ((10, 4), (8, 3)) and D == 3 else 5e-9
+    assert global_rel_err(out.cpu().numpy(), ref).max() <= tol
