@@ -139,6 +139,9 @@ int mtg_compute_cost_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, c
 int mtg_solve_linear_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
                                     const double* d_fixed, double* coeffs, double* d_free,
                                     int32_t* status);
+int mtg_solve_waypoints_nfabian_batch_host_f64(mtg_handle* h, int32_t N, int32_t r, int32_t K, int32_t D, int64_t B,
+                                               const double* positions, double v_max, double a_max, double magic,
+                                               double* coeffs, double* seg_times_out, int32_t* status);
 int mtg_coeffs_from_constraints_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B,
                                                const double* seg_times, const double* d_fixed,
                                                const double* d_free, double* coeffs);

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "mtg_coeffs_from_constraints_batch_host_f64", "mtg_compute_cost_batch_host_f64",
     "mtg_host_alloc", "mtg_host_free", "mtg_device_alloc", "mtg_device_free", "mtg_memcpy_h2d",
     "mtg_memcpy_d2h", "mtg_stream_synchronize", "mtg_version", "mtg_set_option",
-    "mtg_solve_waypoints_nfabian_batch_f64",
+    "mtg_solve_waypoints_nfabian_batch_f64", "mtg_solve_waypoints_nfabian_batch_host_f64",
 ]
 
 
@@ -77,6 +77,8 @@ def load():
     L.mtg_stream_synchronize.argtypes = [vp, vp]
     L.mtg_version.restype = C.c_int
     L.mtg_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.mtg_solve_waypoints_nfabian_batch_host_f64.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i64, dp,
+                                                             C.c_double, C.c_double, C.c_double, dp, dp, dp]
     L.mtg_solve_waypoints_nfabian_batch_f64.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i64, dp,
                                                         C.c_double, C.c_double, C.c_double, dp, dp, dp, vp]
     for name in EXPORTED_SYMBOLS:

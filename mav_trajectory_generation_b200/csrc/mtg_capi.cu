@@ -637,6 +637,46 @@ int mtg_solve_linear_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t
   return host_pipeline(h, p, B, seg_times, d_fixed, nullptr, coeffs, d_free, status, false);
 }
 
+int mtg_solve_waypoints_nfabian_batch_host_f64(mtg_handle* h, int32_t N, int32_t r, int32_t K, int32_t D, int64_t B,
+                                               const double* positions, double v_max, double a_max, double magic,
+                                               double* coeffs, double* seg_times_out, int32_t* status) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  mtg_problem p = {N, r, K, D, nullptr};
+  if (!valid_problem(&p) || B < 0 || (B > 0 && (!positions || !coeffs))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  if (B == 0) return MTG_OK;
+  DeviceGuard g(h->device);
+  const size_t b_pos = size_t(K + 1) * D * 8, b_coef = size_t(K) * D * N * 8, b_t = size_t(K) * 8;
+  int64_t chunk = std::max<int64_t>(1, std::min<int64_t>((B + mtg_handle::kPipe - 1) / mtg_handle::kPipe, 32768));
+  if (B <= 4096) chunk = B;
+  int slot = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += chunk, slot = (slot + 1) % mtg_handle::kPipe) {
+    const int64_t nb = std::min<int64_t>(chunk, B - b0);
+    const size_t o_coef = align_up(b_pos * nb), o_t = align_up(o_coef + b_coef * nb), o_stat = align_up(o_t + b_t * nb);
+    int rc = ensure_pipe(h, slot, align_up(o_stat + 4 * nb));
+    if (rc != MTG_OK) return rc;
+    cudaStream_t s = h->streams[slot];
+    char* base = static_cast<char*>(h->dev_buf[slot]);
+    MTG_CUDA(h, cudaMemcpyAsync(base, positions + b0 * (K + 1) * D, b_pos * nb, cudaMemcpyHostToDevice, s));
+    rc = mtg_solve_waypoints_nfabian_batch_f64(h, N, r, K, D, nb, reinterpret_cast<double*>(base), v_max, a_max, magic,
+                                               reinterpret_cast<double*>(base + o_coef),
+                                               reinterpret_cast<double*>(base + o_t),
+                                               reinterpret_cast<int32_t*>(base + o_stat), s);
+    if (rc != MTG_OK) return rc;
+    MTG_CUDA(h, cudaMemcpyAsync(coeffs + b0 * K * D * N, base + o_coef, b_coef * nb, cudaMemcpyDeviceToHost, s));
+    if (seg_times_out)
+      MTG_CUDA(h, cudaMemcpyAsync(seg_times_out + b0 * K, base + o_t, b_t * nb, cudaMemcpyDeviceToHost, s));
+    if (status) MTG_CUDA(h, cudaMemcpyAsync(status + b0, base + o_stat, 4 * nb, cudaMemcpyDeviceToHost, s));
+    const int next = (slot + 1) % mtg_handle::kPipe;
+    if (b0 + chunk < B && h->streams[next]) MTG_CUDA(h, cudaStreamSynchronize(h->streams[next]));
+  }
+  for (int i = 0; i < mtg_handle::kPipe; ++i)
+    if (h->streams[i]) MTG_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  return MTG_OK;
+}
+
 int mtg_coeffs_from_constraints_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B,
                                                const double* seg_times, const double* d_fixed,
                                                const double* d_free, double* coeffs) {

@@ -86,6 +86,9 @@ class BatchCore {
                          int r);
   bool setupFromWaypoints(size_t B, size_t K, const double* positions, const double* times, int r);
   bool solveLinear();
+  // time allocation (Nfabian) + packing + solve in one device pass; fills times_ and coeffs_
+  bool solveWaypointsNfabian(size_t B, size_t K, const double* positions, int r, double v_max, double a_max,
+                             double magic);
   std::vector<double> computeCosts() const;
   void getSegments(size_t b, Segment::Vector* segments) const;
 

@@ -36,6 +36,15 @@ class BatchPolynomialOptimization {
     return core_.setupFromWaypoints(batch, n_segments, positions, segment_times, derivative_to_optimize);
   }
   bool solveLinear() { return core_.solveLinear(); }
+  // estimateSegmentTimesNfabian(v_max, a_max, magic) + packing + solve fused on the device;
+  // afterwards getSegments()/coefficients() hold the result and segmentTimes() the allocated times.
+  bool solveWaypointsNfabian(size_t batch, size_t n_segments, const double* positions, double v_max, double a_max,
+                             double magic_fabian_constant = 6.5,
+                             int derivative_to_optimize = kHighestDerivativeToOptimize) {
+    return core_.solveWaypointsNfabian(batch, n_segments, positions, derivative_to_optimize, v_max, a_max,
+                                       magic_fabian_constant);
+  }
+  const double* segmentTimes() const { return core_.times_; }  // [B][K]
 
   size_t size() const { return core_.B_; }
   size_t getDimension() const { return core_.dimension_; }

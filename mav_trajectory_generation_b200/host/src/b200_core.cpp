@@ -473,6 +473,23 @@ bool BatchCore::solveLinear() {
   return true;
 }
 
+bool BatchCore::solveWaypointsNfabian(size_t B, size_t K, const double* positions, int r, double v_max, double a_max,
+                                      double magic) {
+  // topology bookkeeping + buffers exactly as setupFromWaypoints (d_fixed_ is still filled so that
+  // getFixedConstraints-style consumers see the same data), but times and the solve come from the device
+  std::vector<double> dummy_times(B * K, 1.0);
+  if (!setupFromWaypoints(B, K, positions, dummy_times.data(), r)) return false;
+  HandleLock lock;
+  mtg_handle* h = defaultHandle();
+  const int rc = mtg_solve_waypoints_nfabian_batch_host_f64(h, N_, r, topo_.K, topo_.D, static_cast<int64_t>(B), positions,
+                                                            v_max, a_max, magic, coeffs_, times_, status_);
+  if (rc != MTG_OK) {
+    LOG(ERROR) << "mtg_solve_waypoints_nfabian_batch_host_f64 failed (rc=" << rc << "): " << mtg_last_error(h);
+    return false;
+  }
+  return true;
+}
+
 std::vector<double> BatchCore::computeCosts() const {
   std::vector<double> cost(B_, 0.0);
   mtg_problem p = {N_, topo_.r, topo_.K, topo_.D, topo_.mask.data()};

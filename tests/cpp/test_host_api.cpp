@@ -305,6 +305,35 @@ static void testBatchMatchesSingle() {
   }
 }
 
+// Fused time allocation + solve equals estimateSegmentTimes() on the host followed by the batch solve.
+static void testFusedWaypointSolve() {
+  const int D = 3, K = 6, B = 19;
+  Eigen::VectorXd lo = Eigen::VectorXd::Constant(D, -10.0), hi = Eigen::VectorXd::Constant(D, 10.0);
+  std::vector<double> positions, times;
+  for (int b = 0; b < B; ++b) {
+    Vertex::Vector v = createRandomVertices(4, K, lo, hi, 7000 + b);
+    std::vector<double> t = estimateSegmentTimesNfabian(v, 3.0, 5.0);
+    times.insert(times.end(), t.begin(), t.end());
+    for (const Vertex& vert : v) {
+      Eigen::VectorXd p;
+      vert.getConstraint(derivative_order::POSITION, &p);
+      for (int d = 0; d < D; ++d) positions.push_back(p[d]);
+    }
+  }
+  BatchPolynomialOptimization<N> a(D), b(D);
+  EXPECT(a.setupFromWaypoints(B, K, positions.data(), times.data()));
+  EXPECT(a.solveLinear());
+  EXPECT(b.solveWaypointsNfabian(B, K, positions.data(), 3.0, 5.0));
+  for (int i = 0; i < B * K; ++i) EXPECT_NEAR(b.segmentTimes()[i], times[i], 4e-16 * times[i]);
+  double scale = 0.0, diff = 0.0;
+  for (int i = 0; i < B * K * D * N; ++i) {
+    scale = std::max(scale, std::abs(a.coefficients()[i]));
+    diff = std::max(diff, std::abs(a.coefficients()[i] - b.coefficients()[i]));
+  }
+  EXPECT(diff <= 1e-12 * scale);
+  for (int i = 0; i < B; ++i) EXPECT(b.status()[i] == 0);
+}
+
 int main(int argc, char** argv) {
   const bool cpu_only = argc > 1 && std::strcmp(argv[1], "--cpu-only") == 0;
   testValueTypesAndFixtures();
@@ -316,6 +345,7 @@ int main(int argc, char** argv) {
     for (const Params& p : kParams) testUnconstrainedLinear(p);
     for (const Params& p : kParams) testConstraintPacking(p);
     testBatchMatchesSingle();
+    testFusedWaypointSolve();
   }
   std::printf("%s: %d checks, %d failures\n", cpu_only ? "cpu-only" : "full", g_checks, g_failures);
   return g_failures == 0 ? 0 : 1;
