@@ -263,10 +263,11 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
       size_t best_smem = 0;
       const int col_options[] = {512, 256, 128, 64, 32, 0};
       for (int cols : col_options) {
-        const int ntm = cols ? std::min(nmax, cols / (2 * e->slots)) : 0;
+        const int tslots = e->slots + e->D;  // TMEM kernel also keeps the vertex position in the state block
+        const int ntm = cols ? std::min(nmax, cols / (2 * tslots)) : 0;
         if (cols && ntm == 0) continue;
         const size_t smem = 16 + size_t(4) * e->stage_bytes_per_warp + size_t(2) * (1 + p->D) * mtg::kTmemThreads * 8 +
-                            size_t(nmax - ntm) * e->slots * mtg::kTmemThreads * sizeof(double);
+                            size_t(nmax - ntm) * tslots * mtg::kTmemThreads * sizeof(double);
         if (smem > h->smem_optin) continue;
         int ctas = std::min<int>(by_regs, int((228 * 1024) / (smem + 1024)));
         ctas = std::min(ctas, 16);

@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
   constexpr int h = N / 2;
   constexpr int m = h - 1;
   constexpr int kL = m * (m + 1) / 2;
-  constexpr int kSlots = kL + m * D;
+  // per eliminated vertex: L (strictly lower) + inverse pivots + y + the vertex position (so that the
+  // outward sweep does not re-read it from global memory)
+  constexpr int kSlots = kL + m * D + D;
   constexpr int kWords = 2 * kSlots;
   constexpr unsigned kFull = 0xffffffffu;
   constexpr int kWarps = kTmemThreads / 32;
@@ -463,6 +465,8 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
         for (int j = 0; j < m; ++j)
 #pragma unroll
           for (int d = 0; d < D; ++d) sv[slot++] = yp[j][d];
+#pragma unroll
+        for (int d = 0; d < D; ++d) sv[slot++] = xc[d];  // position of the vertex just eliminated
       }
 #pragma unroll
       for (int a = 0; a < m; ++a) {
@@ -581,7 +585,16 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
   }
   if (half == 0) store_free(nh + 1, ed);
 
-  pf_issue(nh & 1, nh, nh);  // inputs of the first outward step (or of the final emission when nh == 0)
+  // outward steps take the vertex position from the sweep state; only the segment time is prefetched
+  // (and the position of own vertex 0 for the final emission)
+  auto pf_issue_out = [&](int j) {
+    if (j == 0) {
+      pf_issue(0, 0, 0);
+    } else {
+      if constexpr (!FUSED) cp_async8(PF(j & 1, 0), tt + seg(j));
+    }
+  };
+  pf_issue_out(nh);
 
   for (int v = nmax; v >= 1; --v) {
     double sv[kSlots];
@@ -593,7 +606,7 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
       cp_async_wait_all();
       double xv[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) xv[d] = *PF(v & 1, 1 + d);
+      for (int d = 0; d < D; ++d) xv[d] = sv[kL + m * D + d];
       if constexpr (FUSED) {
         double xe[D];
 #pragma unroll
@@ -603,7 +616,7 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
       } else {
         T = *PF(v & 1, 0);
       }
-      pf_issue((v - 1) & 1, v - 1, v - 1);
+      pf_issue_out(v - 1);
       iT = fast_rcp(T);
       double L[m][m], inv[m], rhs[m][D];
       {
