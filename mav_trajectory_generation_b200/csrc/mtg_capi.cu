@@ -267,6 +267,7 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
         const int ntm = cols ? std::min(nmax, cols / (2 * tslots)) : 0;
         if (cols && ntm == 0) continue;
         const size_t smem = 16 + size_t(4) * e->stage_bytes_per_warp + size_t(2) * (1 + p->D) * mtg::kTmemThreads * 8 +
+                            size_t(nmax + 1) * mtg::kTmemThreads * 8 +
                             size_t(nmax - ntm) * tslots * mtg::kTmemThreads * sizeof(double);
         if (smem > h->smem_optin) continue;
         int ctas = std::min<int>(by_regs, int((228 * 1024) / (smem + 1024)));

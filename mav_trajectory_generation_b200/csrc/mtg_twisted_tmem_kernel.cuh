@@ -188,9 +188,13 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
   // consumer would wait for the NEW loads as well (measured: 25 % of all stall samples).
   double* pf = reinterpret_cast<double*>(smem_raw + 16 + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>()) + threadIdx.x;
   auto PF = [&](int buf, int slot) -> double* { return pf + (size_t(buf) * (1 + D) + slot) * kTmemThreads; };
-  double* spill = reinterpret_cast<double*>(smem_raw + 16 + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>() +
+  // per-thread history of the own-frame segment times seen by the inward sweep (nmax+1 doubles): the
+  // outward sweep reads them back from shared memory (in FUSED mode this also saves the sqrt/exp)
+  double* thist = reinterpret_cast<double*>(smem_raw + 16 + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>() +
                                             tmem_prefetch_bytes<D>()) +
                   threadIdx.x;
+  auto HT = [&](int j) -> double& { return thist[size_t(j) * kTmemThreads]; };
+  double* spill = thist + size_t(nmax + 1) * kTmemThreads;
   auto SP = [&](int blk, int slot) -> double& { return spill[(size_t(blk) * kSlots + slot) * kTmemThreads]; };
 
   // ---- tensor memory for the sweep state
@@ -337,6 +341,7 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
       T0 = __ldg(tt + seg(0));
     }
     if (!(T0 > 0.0)) stat |= kStatusBadTime;
+    HT(0) = T0;
     const double iT0 = fast_rcp(T0);
     double pw[N - 1];
     segment_powers<N, R>(T0, iT0, pw);
@@ -382,6 +387,7 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
       } else {
         T = *PF(v & 1, 0);
       }
+      HT(v) = T;
       {  // prefetch the next step's inputs (clamped indices: never out of bounds)
         const int jn = v + 1 < K ? v + 1 : K - 1;
         const int vn = v + 2 <= K ? v + 2 : K;
@@ -588,11 +594,7 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
   // outward steps take the vertex position from the sweep state; only the segment time is prefetched
   // (and the position of own vertex 0 for the final emission)
   auto pf_issue_out = [&](int j) {
-    if (j == 0) {
-      pf_issue(0, 0, 0);
-    } else {
-      if constexpr (!FUSED) cp_async8(PF(j & 1, 0), tt + seg(j));
-    }
+    if (j == 0) pf_issue(0, 0, 0);  // position of own vertex 0 for the final emission (time comes from HT)
   };
   pf_issue_out(nh);
 
@@ -607,14 +609,9 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
       double xv[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) xv[d] = sv[kL + m * D + d];
+      T = HT(v);
       if constexpr (FUSED) {
-        double xe[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) xe[d] = ed[0][d];
-        T = nfabian_time<D>(xv, xe, prm.v_max, prm.a_max, prm.magic);
         if (tout != nullptr && valid) tout[seg(v)] = T;
-      } else {
-        T = *PF(v & 1, 0);
       }
       pf_issue_out(v - 1);
       iT = fast_rcp(T);
@@ -685,18 +682,9 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
 #pragma unroll
       for (int b = 0; b < m; ++b) sd[1 + b][d] = FUSED ? 0.0 : sgn(b) * __ldg(fx + d * nf + e0 + b);
     }
-    double T;
+    const double T = HT(0);
     if constexpr (FUSED) {
-      double xs[D], xe[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        xs[d] = sd[0][d];
-        xe[d] = ed[0][d];
-      }
-      T = nfabian_time<D>(xs, xe, prm.v_max, prm.a_max, prm.magic);
       if (tout != nullptr && valid) tout[seg(0)] = T;
-    } else {
-      T = *PF(0, 0);
     }
     const double iT = fast_rcp(T);
     __syncwarp();
