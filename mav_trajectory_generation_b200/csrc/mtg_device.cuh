@@ -130,9 +130,25 @@ MTG_DEF_H1(12, 5)
 constexpr int kStatusBadTime = 1;
 constexpr int kStatusNotSpd = 2;
 
-// 1/sqrt(x) and 1/x on the fp64 pipe: MUFU seed + Newton steps (a few ulp; the block Cholesky
-// only needs the inverse pivots).
-__device__ __forceinline__ double fast_rsqrt(double x) { return rsqrt(x); }
-__device__ __forceinline__ double fast_rcp(double x) { return __drcp_rn(x); }
+// 1/sqrt(x) and 1/x: MUFU.RSQ64H / MUFU.RCP64H seed (rsqrt/rcp.approx.ftz.f64) + the same Newton steps
+// the CUDA math library uses, WITHOUT its range checks (pivots and segment times are normal, positive
+// doubles here; zero / negative / NaN inputs still come out as inf / NaN and are reported in status[]).
+// Dropping the checks removes a BSSY/BRA/BSYNC region per call, across which ptxas cannot interleave the
+// independent FMA chains of the block factorisation.  Result within ~1 ulp.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = fma(x, -(y0 * y0), 1.0);           // 1 - x*y0^2
+  const double p = fma(e, 0.375, 0.5);
+  return fma(p, y0 * e, y0);                           // y0 * (1 + e/2 + 3e^2/8)
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+  double e = fma(-x, r0, 1.0);
+  e = fma(e, e, e);
+  const double r1 = fma(r0, e, r0);                    // r0 * (1 + e + e^2)
+  return fma(r1, fma(-x, r1, 1.0), r1);
+}
 
 }  // namespace mtg
