@@ -132,6 +132,14 @@ int mtg_coeffs_from_constraints_batch_f64(mtg_handle* h, const mtg_problem* p, i
 int mtg_compute_cost_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
                                const double* coeffs, double* cost, void* stream);
 
+/* SURVEY.md 8f-2 ("next" row): the nonlinear time optimiser's numerical gradient, batched.
+ * PolynomialOptimizationNonLinear::getCostAndGradientMellinger (reference
+ * impl/polynomial_optimization_nonlinear_impl.h:286-364): cost[b] = computeCost() at seg_times[b], grad[b][n] =
+ * (cost with +0.1 s on segment n and -0.1/(K-1) s on the others, clamped at 0.1 s, re-solved) - cost) / 0.1.
+ * The K+1 solves of every trajectory run as one expanded batch through the same kernels.  cost may be NULL. */
+int mtg_cost_gradient_mellinger_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                                          const double* d_fixed, double* cost, double* grad, void* stream);
+
 /* ---- the hot path, HOST pointers (what PolynomialOptimization<N>::solveLinear() calls) ---- */
 /* Same contract with host buffers; H2D, kernels and D2H are pipelined over internal streams and
  * the call returns when the results are in the host buffers.  Pinned buffers (mtg_host_alloc)

@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "mtg_host_alloc", "mtg_host_free", "mtg_device_alloc", "mtg_device_free", "mtg_memcpy_h2d",
     "mtg_memcpy_d2h", "mtg_stream_synchronize", "mtg_version", "mtg_set_option",
     "mtg_solve_waypoints_nfabian_batch_f64", "mtg_solve_waypoints_nfabian_batch_host_f64",
+    "mtg_cost_gradient_mellinger_batch_f64",
 ]
 
 
@@ -77,6 +78,7 @@ def load():
     L.mtg_stream_synchronize.argtypes = [vp, vp]
     L.mtg_version.restype = C.c_int
     L.mtg_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.mtg_cost_gradient_mellinger_batch_f64.argtypes = [vp, C.POINTER(MtgProblem), i64, dp, dp, dp, dp, vp]
     L.mtg_solve_waypoints_nfabian_batch_host_f64.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i64, dp,
                                                              C.c_double, C.c_double, C.c_double, dp, dp, dp]
     L.mtg_solve_waypoints_nfabian_batch_f64.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i64, dp,
@@ -180,6 +182,18 @@ class Solver:
             status.data_ptr() if status is not None else None, s)
         self._check(rc, "mtg_solve_waypoints_nfabian_batch_f64")
         return coeffs
+
+    def cost_gradient_mellinger(self, prob, seg_times, d_fixed, stream=None):
+        """(cost [B], grad [B][K]) -- batched getCostAndGradientMellinger."""
+        import torch
+        B = seg_times.shape[0]
+        cost = torch.empty((B,), dtype=torch.float64, device=seg_times.device)
+        grad = torch.empty((B, prob.K), dtype=torch.float64, device=seg_times.device)
+        s = stream if stream is not None else torch.cuda.current_stream(seg_times.device).cuda_stream
+        rc = self.lib.mtg_cost_gradient_mellinger_batch_f64(self.h, C.byref(prob.c), B, seg_times.data_ptr(),
+                                                            d_fixed.data_ptr(), cost.data_ptr(), grad.data_ptr(), s)
+        self._check(rc, "mtg_cost_gradient_mellinger_batch_f64")
+        return cost, grad
 
     def coeffs_from_constraints(self, prob, seg_times, d_fixed, d_free, coeffs=None, stream=None):
         import torch

@@ -568,6 +568,69 @@ int mtg_compute_cost_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, c
   return MTG_OK;
 }
 
+int mtg_cost_gradient_mellinger_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                                          const double* d_fixed, double* cost, double* grad, void* stream) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  if (!valid_problem(p) || B < 0 || (B > 0 && (!seg_times || !d_fixed || !grad))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  if (B == 0) return MTG_OK;
+  DeviceGuard g(h->device);
+  CachedTopology* topo = get_topology(h, p);
+  if (!topo) return MTG_ERR_CUDA;
+  const Layout& L = topo->layout;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t K = p->K, D = p->D, N = p->N, nf = L.n_fixed;
+  const size_t per_x = (K + D * nf + K * D * N + 1) * 8;  // times + d_fixed + coeffs + cost of one expanded problem
+  int64_t chunk = std::max<int64_t>(1, int64_t((size_t(384) << 20) / (per_x * (K + 1))));
+  chunk = std::min<int64_t>(chunk, B);
+  const size_t need = per_x * (K + 1) * size_t(chunk);
+  if (need > h->pack_scratch_bytes) {
+    if (h->pack_scratch) {
+      MTG_CUDA(h, cudaDeviceSynchronize());
+      cudaFree(h->pack_scratch);
+      h->pack_scratch = nullptr;
+      h->pack_scratch_bytes = 0;
+    }
+    MTG_CUDA(h, cudaMalloc(&h->pack_scratch, need));
+    h->pack_scratch_bytes = need;
+  }
+  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+    const int64_t nb = std::min<int64_t>(chunk, B - b0), nx = nb * int64_t(K + 1);
+    double* t_x = h->pack_scratch;
+    double* f_x = t_x + size_t(nx) * K;
+    double* c_x = f_x + size_t(nx) * D * nf;
+    double* j_x = c_x + size_t(nx) * K * D * N;
+    mtg::MellingerParams mp;
+    mp.K = p->K;
+    mp.D = p->D;
+    mp.n_fixed = L.n_fixed;
+    mp.B = nb;
+    mp.times = seg_times + b0 * K;
+    mp.dfix = d_fixed + b0 * D * nf;
+    mp.times_x = t_x;
+    mp.dfix_x = f_x;
+    mp.increment = 0.1;  // reference: increment_time (nonlinear_impl.h:310)
+    mp.lower = 0.1;      // kOptimizationTimeLowerBound (polynomial_optimization_nonlinear.h:31)
+    const int threads = 128;
+    const int64_t blocks = std::min<int64_t>((nx + threads - 1) / threads, int64_t(h->sm_count) * 16);
+    mtg::mellinger_expand_kernel<<<(unsigned)blocks, threads, 0, s>>>(mp);
+    MTG_CUDA(h, cudaGetLastError());
+    h->launches++;
+    int rc = launch_solve(h, p, topo, nx, t_x, f_x, nullptr, c_x, nullptr, nullptr, s, false);
+    if (rc != MTG_OK) return rc;
+    rc = mtg_compute_cost_batch_f64(h, p, nx, t_x, c_x, j_x, s);
+    if (rc != MTG_OK) return rc;
+    const int64_t gb = std::min<int64_t>((nb + threads - 1) / threads, int64_t(h->sm_count) * 16);
+    mtg::mellinger_gradient_kernel<<<(unsigned)gb, threads, 0, s>>>(nb, p->K, j_x, cost ? cost + b0 : nullptr,
+                                                                  grad + b0 * K, mp.increment);
+    MTG_CUDA(h, cudaGetLastError());
+    h->launches++;
+  }
+  return MTG_OK;
+}
+
 // ---- host-pointer variants: chunked H2D -> kernel -> D2H over kPipe streams ---------------
 static int host_pipeline(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
                          const double* d_fixed, const double* d_free_in, double* coeffs, double* d_free_out,

@@ -245,6 +245,55 @@ __global__ void __launch_bounds__(128) nfabian_pack_kernel(const PackParams prm)
   }
 }
 
+// Batched getCostAndGradientMellinger (reference impl/polynomial_optimization_nonlinear_impl.h:286-364):
+// every trajectory is expanded into K+1 problems -- the current segment times and, for each segment n,
+// the times with +increment on n and -increment/(K-1) on the others, clamped at `lower` -- which are then
+// solved and costed by the regular kernels in ONE launch each; the gradient is the forward difference.
+struct MellingerParams {
+  int K, D, n_fixed;
+  long long B;
+  const double* __restrict__ times;   // [B][K]
+  const double* __restrict__ dfix;    // [B][D][n_fixed]
+  double* __restrict__ times_x;       // [B*(K+1)][K]
+  double* __restrict__ dfix_x;        // [B*(K+1)][D][n_fixed]
+  double increment, lower;
+};
+
+__global__ void __launch_bounds__(128) mellinger_expand_kernel(const MellingerParams prm) {
+  const int K = prm.K, dnf = prm.D * prm.n_fixed;
+  const long long total = prm.B * (K + 1);
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < total; row += nthreads) {
+    const long long b = row / (K + 1);
+    const int n = int(row - b * (K + 1)) - 1;  // -1: unperturbed
+    const double* __restrict__ t = prm.times + b * K;
+    double* __restrict__ tx = prm.times_x + row * K;
+    const double corr = prm.increment / (K - 1.0);
+    for (int i = 0; i < K; ++i) {
+      double v = t[i];
+      if (n >= 0) {
+        v = (i == n) ? v + prm.increment : v - corr;
+        v = v > prm.lower ? v : prm.lower;  // std::max(lower, t)
+      }
+      tx[i] = v;
+    }
+    const double* __restrict__ f = prm.dfix + b * dnf;
+    double* __restrict__ fxp = prm.dfix_x + row * dnf;
+    for (int c = 0; c < dnf; ++c) fxp[c] = f[c];
+  }
+}
+
+__global__ void __launch_bounds__(128) mellinger_gradient_kernel(long long B, int K, const double* __restrict__ cost_x,
+                                                                 double* __restrict__ cost, double* __restrict__ grad,
+                                                                 double increment) {
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += nthreads) {
+    const double J = cost_x[b * (K + 1)];
+    if (cost) cost[b] = J;
+    for (int n = 0; n < K; ++n) grad[b * K + n] = K == 1 ? 0.0 : (cost_x[b * (K + 1) + 1 + n] - J) / increment;
+  }
+}
+
 // computeCost() (linear_impl.h:123-140): 0.5 * sum c^T Q(T) c with
 // Q[a][b] = 2 B(r,a) B(r,b) T^(a+b-2r+1) / (a+b-2r+1)   (:567-583).
 struct CostParams {

@@ -621,6 +621,35 @@ void oracle_make_waypoint_batch(int K, int D, int64_t B, double lo, double hi, u
   }
 }
 
+// getCostAndGradientMellinger (reference impl/polynomial_optimization_nonlinear_impl.h:286-364): cost of the
+// current times and the forward-difference gradient with the total-time-preserving perturbation
+// (+0.1 s on segment n, -0.1/(K-1) on the others, clamped at kOptimizationTimeLowerBound = 0.1,
+// polynomial_optimization_nonlinear.h:31).  Waypoint topology.
+int oracle_cost_gradient_mellinger(int N, int r, int K, int D, const double* positions, const double* times,
+                                   double* cost, double* grad) {
+  std::vector<uint8_t> mask;
+  std::vector<double> values;
+  waypoint_problem(N, K, D, positions, &mask, &values);
+  Problem p(N, D);
+  if (!p.setup(K, mask.data(), values.data(), times, r) || !p.solve_linear()) return -1;
+  const double J = p.compute_cost();
+  *cost = J;
+  if (K == 1) {
+    grad[0] = 0.0;
+    return 0;
+  }
+  const double increment_time = 0.1, lower = 0.1;
+  std::vector<double> bigger(K);
+  for (int n = 0; n < K; ++n) {
+    const double corr = increment_time / (K - 1.0);
+    for (int i = 0; i < K; ++i) bigger[i] = (i == n) ? times[i] + increment_time : times[i] - corr;
+    for (double& t : bigger) t = std::max(lower, t);
+    if (!p.update_segment_times(bigger.data()) || !p.solve_linear()) return -2;
+    grad[n] = (p.compute_cost() - J) / increment_time;
+  }
+  return 0;
+}
+
 int oracle_hardware_threads() { return int(std::thread::hardware_concurrency()); }
 
 }  // extern "C"

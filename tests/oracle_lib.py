@@ -45,6 +45,8 @@ def lib():
                                                   C.c_void_p, C.c_int, C.c_int]
         L.oracle_make_waypoint_batch.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double, C.c_uint64,
                                                  C.c_double, C.c_double, _dp, _dp]
+        L.oracle_cost_gradient_mellinger.restype = C.c_int
+        L.oracle_cost_gradient_mellinger.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         L.oracle_hardware_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -183,3 +185,16 @@ def waypoint_d_fixed(N, positions, start_derivs=None, end_derivs=None):
     if end_derivs is not None:
         out[:, :, h + K:] = np.transpose(end_derivs, (0, 2, 1))
     return out
+
+
+def cost_gradient_mellinger(N, r, positions, times):
+    """One trajectory: (cost, grad[K]) as PolynomialOptimizationNonLinear::getCostAndGradientMellinger."""
+    positions = np.ascontiguousarray(positions, dtype=np.float64)
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    K = times.shape[0]
+    cost = np.zeros(1)
+    grad = np.zeros(K)
+    rc = lib().oracle_cost_gradient_mellinger(N, r, K, positions.shape[1], positions, times, cost, grad)
+    if rc != 0:
+        raise RuntimeError(f"oracle_cost_gradient_mellinger rc={rc}")
+    return float(cost[0]), grad
