@@ -140,6 +140,14 @@ int mtg_compute_cost_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, c
 int mtg_cost_gradient_mellinger_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
                                           const double* d_fixed, double* cost, double* grad, void* stream);
 
+/* SURVEY.md 8f-3 ("next" row): batched Trajectory::evaluate on a uniform grid t_s = t_start + s*dt,
+ * s < n_samples (reference src/trajectory.cpp:48-79 conventions per sample: a time on a vertex belongs to the
+ * segment on its right, t == total time is the end of the last segment, beyond the end yields zeros;
+ * Horner form of Polynomial::evaluate, polynomial.h:134-149).  coeffs [B][K][D][N] -> out [B][n_samples][D]. */
+int mtg_evaluate_batch_f64(mtg_handle* h, int32_t N, int32_t K, int32_t D, int64_t B, const double* seg_times,
+                           const double* coeffs, int32_t derivative, double t_start, double dt, int32_t n_samples,
+                           double* out, void* stream);
+
 /* ---- the hot path, HOST pointers (what PolynomialOptimization<N>::solveLinear() calls) ---- */
 /* Same contract with host buffers; H2D, kernels and D2H are pipelined over internal streams and
  * the call returns when the results are in the host buffers.  Pinned buffers (mtg_host_alloc)

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "mtg_host_alloc", "mtg_host_free", "mtg_device_alloc", "mtg_device_free", "mtg_memcpy_h2d",
     "mtg_memcpy_d2h", "mtg_stream_synchronize", "mtg_version", "mtg_set_option",
     "mtg_solve_waypoints_nfabian_batch_f64", "mtg_solve_waypoints_nfabian_batch_host_f64",
-    "mtg_cost_gradient_mellinger_batch_f64",
+    "mtg_cost_gradient_mellinger_batch_f64", "mtg_evaluate_batch_f64",
 ]
 
 
@@ -78,6 +78,8 @@ def load():
     L.mtg_stream_synchronize.argtypes = [vp, vp]
     L.mtg_version.restype = C.c_int
     L.mtg_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.mtg_evaluate_batch_f64.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i64, dp, dp, C.c_int32, C.c_double,
+                                         C.c_double, C.c_int32, dp, vp]
     L.mtg_cost_gradient_mellinger_batch_f64.argtypes = [vp, C.POINTER(MtgProblem), i64, dp, dp, dp, dp, vp]
     L.mtg_solve_waypoints_nfabian_batch_host_f64.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i64, dp,
                                                              C.c_double, C.c_double, C.c_double, dp, dp, dp]
@@ -182,6 +184,18 @@ class Solver:
             status.data_ptr() if status is not None else None, s)
         self._check(rc, "mtg_solve_waypoints_nfabian_batch_f64")
         return coeffs
+
+    def evaluate(self, seg_times, coeffs, derivative, t_start, dt, n_samples, stream=None):
+        """coeffs [B][K][D][N] -> samples [B][n_samples][D] of the given derivative (Trajectory::evaluate)."""
+        import torch
+        B, K, D, N = coeffs.shape
+        out = torch.empty((B, n_samples, D), dtype=torch.float64, device=coeffs.device)
+        s = stream if stream is not None else torch.cuda.current_stream(coeffs.device).cuda_stream
+        rc = self.lib.mtg_evaluate_batch_f64(self.h, N, K, D, B, seg_times.data_ptr(), coeffs.data_ptr(),
+                                             int(derivative), float(t_start), float(dt), int(n_samples),
+                                             out.data_ptr(), s)
+        self._check(rc, "mtg_evaluate_batch_f64")
+        return out
 
     def cost_gradient_mellinger(self, prob, seg_times, d_fixed, stream=None):
         """(cost [B], grad [B][K]) -- batched getCostAndGradientMellinger."""

@@ -568,6 +568,38 @@ int mtg_compute_cost_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, c
   return MTG_OK;
 }
 
+int mtg_evaluate_batch_f64(mtg_handle* h, int32_t N, int32_t K, int32_t D, int64_t B, const double* seg_times,
+                           const double* coeffs, int32_t derivative, double t_start, double dt, int32_t n_samples,
+                           double* out, void* stream) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  if (N < 1 || N > MTG_MAX_N || K < 1 || D < 1 || B < 0 || derivative < 0 || n_samples < 0 ||
+      (B > 0 && n_samples > 0 && (!seg_times || !coeffs || !out))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  if (B == 0 || n_samples == 0) return MTG_OK;
+  DeviceGuard g(h->device);
+  mtg::EvalParams ep;
+  ep.N = N;
+  ep.K = K;
+  ep.D = D;
+  ep.derivative = derivative;
+  ep.n_samples = n_samples;
+  ep.B = B;
+  ep.t_start = t_start;
+  ep.dt = dt;
+  ep.times = seg_times;
+  ep.coeffs = coeffs;
+  ep.out = out;
+  const int threads = 256;
+  const int64_t total = B * int64_t(n_samples);
+  const int64_t blocks = std::min<int64_t>((total + threads - 1) / threads, int64_t(h->sm_count) * 32);
+  mtg::evaluate_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(ep);
+  MTG_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return MTG_OK;
+}
+
 int mtg_cost_gradient_mellinger_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
                                           const double* d_fixed, double* cost, double* grad, void* stream) {
   if (!h) return MTG_ERR_BAD_ARG;

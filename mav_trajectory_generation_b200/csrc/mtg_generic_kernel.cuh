@@ -294,6 +294,57 @@ __global__ void __launch_bounds__(128) mellinger_gradient_kernel(long long B, in
   }
 }
 
+// Batched Trajectory::evaluate on a uniform time grid (reference src/trajectory.cpp:48-79 semantics per
+// sample; Polynomial::evaluate Horner form, polynomial.h:134-149).  One thread per (trajectory, sample),
+// samples fastest so that the [B][S][D] output is written coalesced.
+struct EvalParams {
+  int N, K, D, derivative, n_samples;
+  long long B;
+  double t_start, dt;
+  const double* __restrict__ times;   // [B][K]
+  const double* __restrict__ coeffs;  // [B][K][D][N]
+  double* __restrict__ out;           // [B][n_samples][D]
+};
+
+__global__ void __launch_bounds__(256) evaluate_kernel(const EvalParams prm) {
+  const int N = prm.N, K = prm.K, D = prm.D, S = prm.n_samples, der = prm.derivative;
+  const long long total = prm.B * S;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    const long long b = idx / S;
+    const int sidx = int(idx - b * S);
+    const double t = prm.t_start + sidx * prm.dt;
+    const double* __restrict__ tt = prm.times + b * K;
+    double start = 0.0;
+    int i = 0;
+    for (; i < K; ++i) {
+      const double Ti = tt[i];
+      if (start + Ti > t) break;
+      start += Ti;
+    }
+    bool in_range = true;
+    if (i == K) {
+      if (t > start) in_range = false;
+      i = K - 1;
+      start -= tt[i];
+    }
+    const double tl = t - start;
+    double* __restrict__ o = prm.out + idx * D;
+    for (int d = 0; d < D; ++d) {
+      double acc = 0.0;
+      if (in_range && der < N) {
+        const double* __restrict__ c = prm.coeffs + ((b * K + i) * D + d) * N;
+        for (int j = N - 1; j >= der; --j) {
+          double bc = 1.0;  // B(der, j) = j!/(j-der)!
+          for (int q = 0; q < der; ++q) bc *= double(j - q);
+          acc = fma(acc, tl, bc * c[j]);
+        }
+      }
+      o[d] = acc;
+    }
+  }
+}
+
 // computeCost() (linear_impl.h:123-140): 0.5 * sum c^T Q(T) c with
 // Q[a][b] = 2 B(r,a) B(r,b) T^(a+b-2r+1) / (a+b-2r+1)   (:567-583).
 struct CostParams {

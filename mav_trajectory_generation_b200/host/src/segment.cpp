@@ -109,14 +109,24 @@ std::vector<double> Trajectory::getSegmentTimes() const {
 
 Eigen::VectorXd Trajectory::evaluate(double t, int derivative_order) const {
   CHECK(!segments_.empty());
-  // walk to the segment containing t; past the end, extrapolate the last segment
-  double t_local = t;
+  // Same conventions as the reference (src/trajectory.cpp:48-79): a time that falls on a vertex belongs to
+  // the segment on its right; t == total time evaluates the end of the last segment; t beyond the end is an
+  // error and yields zeros.
+  double start = 0.0;
   size_t i = 0;
-  while (i + 1 < segments_.size() && t_local > segments_[i].getTime()) {
-    t_local -= segments_[i].getTime();
-    ++i;
+  for (; i < segments_.size(); ++i) {
+    if (start + segments_[i].getTime() > t) break;
+    start += segments_[i].getTime();
   }
-  return segments_[i].evaluate(t_local, derivative_order);
+  if (i == segments_.size()) {
+    if (t > start) {
+      LOG(ERROR) << "Time out of range of the trajectory!";
+      return Eigen::VectorXd::Zero(D_);
+    }
+    i = segments_.size() - 1;
+    start -= segments_[i].getTime();
+  }
+  return segments_[i].evaluate(t - start, derivative_order);
 }
 
 void Trajectory::evaluateRange(double t_start, double t_end, double dt, int derivative_order,

@@ -368,3 +368,40 @@ def test_batched_mellinger_gradient(solver, oracle, N, r, K, D, B):
         c_ref, g_ref = oracle.cost_gradient_mellinger(N, r, pos[b], times[b])
         assert abs(cost[b] - c_ref) <= 1e-8 * abs(c_ref)
         assert np.abs(grad[b] - g_ref).max() <= 1e-6 * max(abs(c_ref), np.abs(g_ref).max())
+
+
+def test_batched_evaluate(solver, oracle):
+    """SURVEY.md 8f-3: batched Trajectory::evaluate against a numpy Horner evaluation with the reference's
+    segment-selection conventions (vertex times belong to the right segment, the end time to the last one,
+    beyond the end -> zeros)."""
+    import torch
+    import mav_trajectory_generation_b200 as m
+    N, r, K, D, B = 10, 4, 6, 3, 37
+    pos, times = oracle.make_waypoint_batch(K, D, B, base_seed=8000)
+    prob = m.Problem(N, r, K, D)
+    t_d = torch.from_numpy(times).cuda()
+    coeffs = solver.solve_linear(prob, t_d, torch.from_numpy(oracle.waypoint_d_fixed(N, pos)).cuda())
+    c = coeffs.cpu().numpy()
+    S, dt = 257, 0.25
+    for der in (0, 1, 2, 4):
+        got = solver.evaluate(t_d, coeffs, der, 0.0, dt, S).cpu().numpy()
+        want = np.zeros((B, S, D))
+        for b in range(B):
+            ends = np.cumsum(times[b])
+            for s_i in range(S):
+                t = s_i * dt
+                if t > ends[-1]:
+                    continue
+                i = int(np.searchsorted(ends, t, side="right"))
+                i = min(i, K - 1)
+                tl = t - (ends[i] - times[b, i])
+                for d in range(D):
+                    acc = 0.0
+                    for j in range(N - 1, der - 1, -1):
+                        acc = acc * tl + np.prod(np.arange(j - der + 1, j + 1, dtype=np.float64)) * c[b, i, d, j]
+                    want[b, s_i, d] = acc
+        scale = max(1.0, np.abs(want).max())
+        assert np.abs(got - want).max() <= 1e-11 * scale, der
+    # positions at the vertices are the waypoints (t on a vertex -> right segment, value continuous)
+    pos0 = solver.evaluate(t_d, coeffs, 0, 0.0, 1.0, 1).cpu().numpy()[:, 0, :]
+    assert np.abs(pos0 - pos[:, 0, :]).max() <= 1e-9
