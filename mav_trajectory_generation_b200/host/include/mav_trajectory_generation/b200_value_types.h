@@ -1,0 +1,284 @@
+// b200_value_types.h -- the value types of the reference's public API in ONE header:
+// derivative_order (reference motion_defines.h), Polynomial (polynomial.h, data half), Vertex (vertex.h),
+// Segment (segment.h, data half), Trajectory (trajectory.h, container half).  The reference's per-class
+// header names (vertex.h, segment.h, ...) are kept as forwarding headers so existing #include lines work.
+#ifndef MAV_TRAJECTORY_GENERATION_B200_VALUE_TYPES_H_
+#define MAV_TRAJECTORY_GENERATION_B200_VALUE_TYPES_H_
+
+#include <cstdint>
+#include <map>
+#include <ostream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "mav_trajectory_generation/eigen_shim.h"
+#include "mav_trajectory_generation/glog_shim.h"
+
+// ===== motion_defines ============================================================
+// motion_defines.h -- names of the position derivatives (mirror of the reference's
+// include/mav_trajectory_generation/motion_defines.h:25-47; same constants, same namespace).
+
+
+namespace mav_trajectory_generation {
+namespace derivative_order {
+static constexpr int INVALID = -1;
+static constexpr int POSITION = 0, VELOCITY = 1, ACCELERATION = 2, JERK = 3, SNAP = 4;
+static constexpr int ORIENTATION = 0, ANGULAR_VELOCITY = 1, ANGULAR_ACCELERATION = 2;
+}  // namespace derivative_order
+
+std::string positionDerivativeToString(int derivative);
+int positionDerivativeToInt(const std::string& string);
+std::string orintationDerivativeToString(int derivative);  // (sic) reference spelling
+int orientationDerivativeToInt(const std::string& string);
+}  // namespace mav_trajectory_generation
+
+// ===== polynomial ============================================================
+// polynomial.h -- value type for one polynomial (mirror of the data half of the reference's
+// include/mav_trajectory_generation/polynomial.h:37-251: coefficients in INCREASING powers,
+// evaluation, derivative coefficients, the base-coefficient table).  The root-finding half of
+// the reference class (Jenkins-Traub extrema, polynomial.h:151-186) is outside the hot path
+//  and is not provided.
+
+
+
+namespace mav_trajectory_generation {
+
+class Polynomial {
+ public:
+  typedef std::vector<Polynomial> Vector;
+
+  static constexpr int kMaxN = 12;                          // reference polynomial.h:44
+  static constexpr int kMaxConvolutionSize = 2 * kMaxN - 2;  // :47
+  // base_coefficients_(d, j) = j! / (j - d)!  (reference polynomial.h:50, polynomial.cpp:145-160)
+  static Eigen::MatrixXd base_coefficients_;
+
+  explicit Polynomial(int N) : N_(N), coefficients_(Eigen::VectorXd::Zero(N)) {}
+  Polynomial(int N, const Eigen::VectorXd& coeffs) : N_(N), coefficients_(coeffs) {
+    CHECK_EQ(N_, static_cast<int>(coeffs.size())) << "Number of coefficients has to match.";
+  }
+  explicit Polynomial(const Eigen::VectorXd& coeffs) : N_(static_cast<int>(coeffs.size())), coefficients_(coeffs) {}
+
+  int N() const { return N_; }
+  bool operator==(const Polynomial& rhs) const { return coefficients_ == rhs.coefficients_; }
+  bool operator!=(const Polynomial& rhs) const { return !(*this == rhs); }
+  Polynomial operator+(const Polynomial& rhs) const { return Polynomial(coefficients_ + rhs.coefficients_); }
+  Polynomial& operator+=(const Polynomial& rhs) {
+    coefficients_ += rhs.coefficients_;
+    return *this;
+  }
+  Polynomial operator*(const Polynomial& rhs) const { return Polynomial(convolve(coefficients_, rhs.coefficients_)); }
+  Polynomial operator*(const double& rhs) const { return Polynomial(coefficients_ * rhs); }
+
+  void setCoefficients(const Eigen::VectorXd& coeffs) {
+    CHECK_EQ(N_, static_cast<int>(coeffs.size())) << "Number of coefficients has to match.";
+    coefficients_ = coeffs;
+  }
+  // Coefficients of the given derivative (same length N, trailing zeros).
+  Eigen::VectorXd getCoefficients(int derivative = 0) const;
+  // Fills derivatives 0 .. result->size()-1 at time t.
+  void evaluate(double t, Eigen::VectorXd* result) const;
+  // One derivative at time t.
+  double evaluate(double t, int derivative) const;
+
+  bool getPolynomialWithAppendedCoefficients(int new_N, Polynomial* new_polynomial) const;
+  // Row of the mapping matrix: d-th derivative basis evaluated at t (reference polynomial.h:201-219).
+  static void baseCoeffsWithTime(int N, int derivative, double t, Eigen::VectorXd* coeffs);
+  static Eigen::VectorXd baseCoeffsWithTime(int N, int derivative, double t) {
+    Eigen::VectorXd c(N);
+    baseCoeffsWithTime(N, derivative, t, &c);
+    return c;
+  }
+  static Eigen::VectorXd convolve(const Eigen::VectorXd& data, const Eigen::VectorXd& kernel);
+  static inline int getConvolutionLength(int data_size, int kernel_size) { return data_size + kernel_size - 1; }
+  void scalePolynomialInTime(double scaling_factor);
+  void offsetPolynomial(const double offset);
+
+ private:
+  int N_;
+  Eigen::VectorXd coefficients_;
+};
+
+Eigen::MatrixXd computeBaseCoefficients(int N);
+
+}  // namespace mav_trajectory_generation
+
+// ===== vertex ============================================================
+// vertex.h -- support point of a path with per-derivative constraints (mirror of the
+// reference's include/mav_trajectory_generation/vertex.h:42-177 and src/vertex.cpp).
+
+
+
+namespace mav_trajectory_generation {
+
+class Vertex {
+ public:
+  typedef std::vector<Vertex> Vector;
+  typedef Eigen::VectorXd ConstraintValue;
+  typedef std::pair<int, ConstraintValue> Constraint;
+  typedef std::map<int, ConstraintValue> Constraints;
+
+  explicit Vertex(size_t dimension) : D_(static_cast<int>(dimension)) {}
+  int D() const { return D_; }
+
+  // Same value in every dimension.
+  void addConstraint(int derivative_order, double value) {
+    constraints_[derivative_order] = ConstraintValue::Constant(D_, value);
+  }
+  void addConstraint(int type, const Eigen::VectorXd& constraint);
+  bool removeConstraint(int type);
+  // Position = constraint, derivatives 1..up_to_derivative = 0.
+  void makeStartOrEnd(const Eigen::VectorXd& constraint, int up_to_derivative);
+  void makeStartOrEnd(double value, int up_to_derivative) {
+    makeStartOrEnd(Eigen::VectorXd::Constant(D_, value), up_to_derivative);
+  }
+  bool hasConstraint(int derivative_order) const;
+  bool getConstraint(int derivative_order, Eigen::VectorXd* constraint) const;
+  Constraints::const_iterator cBegin() const { return constraints_.begin(); }
+  Constraints::const_iterator cEnd() const { return constraints_.end(); }
+  size_t getNumberOfConstraints() const { return constraints_.size(); }
+  bool isEqualTol(const Vertex& rhs, double tol) const;
+  bool getSubdimension(const std::vector<size_t>& subdimensions, int max_derivative_order, Vertex* subvertex) const;
+
+ private:
+  int D_;
+  Constraints constraints_;
+};
+
+std::ostream& operator<<(std::ostream& stream, const Vertex& v);
+std::ostream& operator<<(std::ostream& stream, const std::vector<Vertex>& vertices);
+
+std::vector<double> estimateSegmentTimes(const Vertex::Vector& vertices, double v_max, double a_max);
+std::vector<double> estimateSegmentTimesVelocityRamp(const Vertex::Vector& vertices, double v_max, double a_max,
+                                                     double time_factor = 1.0);
+std::vector<double> estimateSegmentTimesNfabian(const Vertex::Vector& vertices, double v_max, double a_max,
+                                                double magic_fabian_constant = 6.5);
+double computeTimeVelocityRamp(const Eigen::VectorXd& start, const Eigen::VectorXd& goal, double v_max,
+                               double a_max);
+inline int getHighestDerivativeFromN(int N) { return N / 2 - 1; }
+
+Vertex::Vector createRandomVertices(int maximum_derivative, size_t n_segments,
+                                    const Eigen::VectorXd& minimum_position,
+                                    const Eigen::VectorXd& maximum_position, size_t seed = 0);
+Vertex::Vector createSquareVertices(int maximum_derivative, const Eigen::Vector3d& center, double side_length,
+                                    int rounds);
+Vertex::Vector createRandomVertices1D(int maximum_derivative, size_t n_segments, double minimum_position,
+                                      double maximum_position, size_t seed = 0);
+}  // namespace mav_trajectory_generation
+
+// ===== segment ============================================================
+// segment.h -- D polynomials sharing one duration (mirror of the data half of the reference's
+// include/mav_trajectory_generation/segment.h:43-128; the extrema search is out of scope).
+
+
+
+namespace mav_trajectory_generation {
+
+constexpr double kNumNSecPerSec = 1.0e9;
+constexpr double kNumSecPerNsec = 1.0e-9;
+
+class Segment {
+ public:
+  typedef std::vector<Segment> Vector;
+
+  Segment(int N, int D) : time_(0.0), N_(N), D_(D) { polynomials_.resize(D_, Polynomial(N_)); }
+  Segment(const Segment& segment) = default;
+  Segment& operator=(const Segment& segment) = default;
+
+  bool operator==(const Segment& rhs) const;
+  bool operator!=(const Segment& rhs) const { return !(*this == rhs); }
+
+  int D() const { return D_; }
+  int N() const { return N_; }
+  double getTime() const { return time_; }
+  uint64_t getTimeNSec() const { return static_cast<uint64_t>(kNumNSecPerSec * time_); }
+  void setTime(double time_sec) { time_ = time_sec; }
+  void setTimeNSec(uint64_t time_ns) { time_ = time_ns * kNumSecPerNsec; }
+
+  Polynomial& operator[](size_t idx);
+  const Polynomial& operator[](size_t idx) const;
+  const Polynomial::Vector& getPolynomialsRef() const { return polynomials_; }
+
+  Eigen::VectorXd evaluate(double t, int derivative_order = derivative_order::POSITION) const;
+
+  bool getSegmentWithSingleDimension(int dimension, Segment* new_segment) const;
+  bool getSegmentWithAppendedDimension(const Segment& segment_to_append, Segment* new_segment) const;
+  bool offsetSegment(const Eigen::VectorXd& A_r_B);
+
+ protected:
+  Polynomial::Vector polynomials_;
+  double time_;
+
+ private:
+  int N_;
+  int D_;
+};
+
+void printSegment(std::ostream& stream, const Segment& s, int derivative);
+std::ostream& operator<<(std::ostream& stream, const Segment& s);
+std::ostream& operator<<(std::ostream& stream, const std::vector<Segment>& segments);
+}  // namespace mav_trajectory_generation
+
+// ===== trajectory ============================================================
+// trajectory.h -- container of segments (mirror of the container half of the reference's
+// include/mav_trajectory_generation/trajectory.h:31-149: what getTrajectory() needs plus
+// evaluation; analytic extrema / time scaling are downstream of the hot path and not provided).
+
+
+
+namespace mav_trajectory_generation {
+
+class Trajectory {
+ public:
+  Trajectory() : D_(0), N_(0), max_time_(0.0) {}
+
+  bool operator==(const Trajectory& rhs) const;
+  bool operator!=(const Trajectory& rhs) const { return !(*this == rhs); }
+
+  int D() const { return D_; }
+  int N() const { return N_; }
+  int K() const { return static_cast<int>(segments_.size()); }
+  bool empty() const { return segments_.empty(); }
+  void clear() {
+    segments_.clear();
+    D_ = N_ = 0;
+    max_time_ = 0.0;
+  }
+  void setSegments(const Segment::Vector& segments) {
+    CHECK(!segments.empty());
+    D_ = segments.front().D();
+    N_ = segments.front().N();
+    max_time_ = 0.0;
+    segments_.clear();
+    addSegments(segments);
+  }
+  void addSegments(const Segment::Vector& segments) {
+    for (const Segment& segment : segments) {
+      CHECK_EQ(segment.D(), D_);
+      CHECK_EQ(segment.N(), N_);
+      max_time_ += segment.getTime();
+    }
+    segments_.insert(segments_.end(), segments.begin(), segments.end());
+  }
+  void getSegments(Segment::Vector* segments) const { *CHECK_NOTNULL(segments) = segments_; }
+  const Segment::Vector& segments() const { return segments_; }
+  double getMinTime() const { return 0.0; }
+  double getMaxTime() const { return max_time_; }
+  std::vector<double> getSegmentTimes() const;
+
+  // Value of one derivative at time t (clamped into the last segment like the reference,
+  // trajectory.cpp:48-79).
+  Eigen::VectorXd evaluate(double t, int derivative_order = derivative_order::POSITION) const;
+  // Samples [t_start, t_end] every dt.
+  void evaluateRange(double t_start, double t_end, double dt, int derivative_order,
+                     std::vector<Eigen::VectorXd>* result, std::vector<double>* sampling_times = nullptr) const;
+
+ private:
+  int D_;
+  int N_;
+  double max_time_;
+  Segment::Vector segments_;
+};
+}  // namespace mav_trajectory_generation
+
+#endif  // MAV_TRAJECTORY_GENERATION_B200_VALUE_TYPES_H_
