@@ -305,13 +305,25 @@ __global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const Waypoi
         ss[k] = tp[k] * s0;
         se[k] = tp[k] * e0;
       }
+      // Upper coefficients in Hermite form: A(1)^-1 = [[L^-1, 0], [-D^-1 C L^-1, D^-1]] and (C L^-1)[k][j] =
+      // 1/(j-k)! (derivative k of the Taylor part at tau = 1), so  q = D^-1 (se - C L^-1 ss):
+      // h(h+1)/2 + h^2 operations instead of 2 h^2, and the 1/(j-k)! factors are mostly dyadic immediates.
+      double ee[h];
+#pragma unroll
+      for (int k = 0; k < h; ++k) {
+        double acc = se[k] - ss[k];
+#pragma unroll
+        for (int j = k + 1; j < h; ++j) {
+          constexpr double kInvFact[6] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0};
+          acc = (j - k == 1) ? acc - ss[j] : fma(-kInvFact[j - k], ss[j], acc);
+        }
+        ee[k] = acc;
+      }
 #pragma unroll
       for (int q = 0; q < h; ++q) {
-        double acc = AI::at(h + q, 0) * ss[0];
+        double acc = AI::at(h + q, h) * ee[0];
 #pragma unroll
-        for (int k = 1; k < h; ++k) acc = fma(AI::at(h + q, k), ss[k], acc);
-#pragma unroll
-        for (int k = 0; k < h; ++k) acc = fma(AI::at(h + q, h + k), se[k], acc);
+        for (int k = 1; k < h; ++k) acc = fma(AI::at(h + q, h + k), ee[k], acc);
         c[h + q] = acc * itp[q];
       }
 #pragma unroll
