@@ -405,3 +405,31 @@ def test_batched_evaluate(solver, oracle):
     # positions at the vertices are the waypoints (t on a vertex -> right segment, value continuous)
     pos0 = solver.evaluate(t_d, coeffs, 0, 0.0, 1.0, 1).cpu().numpy()[:, 0, :]
     assert np.abs(pos0 - pos[:, 0, :]).max() <= 1e-9
+
+
+def test_small_orders_n2_n4(solver, oracle):
+    """N = 2 (piecewise linear: every constraint fixed, back-substitution only) and N = 4 (cubic, velocity free
+    at interior vertices -> generic kernel), the smallest orders the reference template accepts."""
+    import torch
+    import mav_trajectory_generation_b200 as m
+    rng = np.random.RandomState(4)
+    for N, r in ((2, 0), (4, 1), (4, 0)):
+        h = N // 2
+        K, D, B = 5, 3, 21
+        mask = np.zeros((K + 1, h), dtype=np.uint8)
+        mask[:, 0] = 1
+        mask[0, :] = 1
+        mask[-1, :] = 1
+        prob = m.Problem(N, r, K, D, fixed_mask=mask)
+        times = rng.uniform(1.0, 3.0, size=(B, K))
+        values = rng.uniform(-1, 1, size=(B, K + 1, h, D)) * mask[None, :, :, None]
+        ref = np.zeros((B, K, D, N))
+        dfix = np.zeros((B, D, prob.n_fixed))
+        for b in range(B):
+            res = oracle.solve(N, r, mask, values[b], times[b])
+            ref[b], dfix[b] = res["coeffs"], res["d_fixed"]
+        status = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+        out = solver.solve_linear(prob, torch.from_numpy(times).cuda(), torch.from_numpy(dfix).cuda(), status=status)
+        torch.cuda.synchronize()
+        assert (status.cpu().numpy() == 0).all(), (N, r)
+        assert global_rel_err(out.cpu().numpy(), ref).max() <= 1e-11, (N, r)
