@@ -33,3 +33,15 @@ def test_host_api_full_on_gpu():
     out = subprocess.run([build_binary()], capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "0 failures" in out.stdout
+
+
+def test_readme_example_compiles():
+    """examples/readme_example.cpp is the reference README's program with only the include root changed."""
+    from mav_trajectory_generation_b200 import _build
+    _build.build_all()
+    out = os.path.join(ROOT, "tests", "cpp", "readme_example")
+    subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-I", os.path.join(_build.HOST, "include"), "-I",
+                           os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "readme_example.cpp"), "-o", out,
+                           "-L", _build.PKG, "-lmtg_host", "-lmtg_b200",
+                           "-Wl,-rpath,$ORIGIN/../../mav_trajectory_generation_b200"])
+    assert os.path.exists(out)
