@@ -157,7 +157,8 @@ __device__ __forceinline__ void cp_async8(const double* smem_dst, const double* 
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int N, int R, int D, bool FUSED = false>
-__global__ void __launch_bounds__(kTmemThreads) twisted_tmem_kernel(const WaypointParams prm, const TmemLaunch tl) {
+__global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
+    twisted_tmem_kernel(const WaypointParams prm, const TmemLaunch tl) {
   constexpr int h = N / 2;
   constexpr int m = h - 1;
   constexpr int kL = m * (m + 1) / 2;
