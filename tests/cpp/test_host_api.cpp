@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "mav_trajectory_generation/batch_polynomial_optimization.h"
+#include "mav_trajectory_generation/io.h"
 #include "mav_trajectory_generation/polynomial_optimization_linear.h"
 
 using namespace mav_trajectory_generation;
@@ -110,6 +111,45 @@ static void testValueTypesAndFixtures() {
   EXPECT(Polynomial::base_coefficients_(3, 5) == 60.0);
   Eigen::VectorXd conv = Polynomial::convolve(c, c);
   EXPECT(conv.size() == 7 && conv[6] == 16.0 && conv[0] == 1.0);
+}
+
+// YAML schema of the reference (src/io.cpp:126-219): round trip and a hand-written file in the reference layout.
+static void testYamlIo() {
+  Segment::Vector segments;
+  for (int i = 0; i < 3; ++i) {
+    Segment s(10, 3);
+    s.setTimeNSec(3970847830ull + 17ull * i);
+    for (int d = 0; d < 3; ++d) {
+      Eigen::VectorXd c(10);
+      for (int j = 0; j < 10; ++j) c[j] = std::sin(1.0 + i * 31 + d * 7 + j) * std::pow(10.0, -j);
+      s[d] = Polynomial(10, c);
+    }
+    segments.push_back(s);
+  }
+  const std::string yaml = segmentsToYamlString(segments);
+  Segment::Vector back;
+  EXPECT(segmentsFromYamlString(yaml, &back));
+  EXPECT(back.size() == segments.size());
+  for (size_t i = 0; i < back.size() && i < segments.size(); ++i) {
+    EXPECT(back[i].getTimeNSec() == segments[i].getTimeNSec());
+    for (int d = 0; d < 3; ++d) EXPECT(back[i][d] == segments[i][d]);  // %.17g round-trips bit-exactly
+  }
+  const std::string reference_style =
+      "segments:\n"
+      "  - N: 4\n"
+      "    D: 2\n"
+      "    time: 1500000000  # [ns]\n"
+      "    coefficients:\n"
+      "      - [0, 1, 0.5, -0.25]\n"
+      "      - [2, 0, 0, 1e-3]\n";
+  EXPECT(segmentsFromYamlString(reference_style, &back));
+  EXPECT(back.size() == 1 && back[0].N() == 4 && back[0].D() == 2);
+  EXPECT_NEAR(back[0].getTime(), 1.5, 1e-12);
+  EXPECT_NEAR(back[0][1].getCoefficients()[3], 1e-3, 0);
+  EXPECT(!segmentsFromYamlString("trajectory:\n  - N: 4\n", &back));              // no segments element
+  EXPECT(!segmentsFromYamlString("segments:\n  - N: 4\n    D: 2\n", &back));       // missing elements
+  EXPECT(!segmentsFromYamlString(
+      "segments:\n  - N: 4\n    D: 1\n    time: 5\n    coefficients:\n      - [1, 2, 3]\n", &back));  // N mismatch
 }
 
 // AMatrixInversion (test :731-741) -- here A^-1 comes from the exact table scaling.
@@ -339,6 +379,7 @@ int main(int argc, char** argv) {
   testValueTypesAndFixtures();
   testAMatrixInversion();
   testLayoutOnly();
+  testYamlIo();
   if (!cpu_only) {
     testTwoVerticesSetup();
     testReadmeExample();
