@@ -133,9 +133,9 @@ struct WaypointEntry {
   int N, R, D, slots;
   WaypointKernel fn;          // one thread per trajectory
   WaypointKernel fn_twisted;  // two lanes per trajectory (twisted factorisation)
-  void (*fn_tmem)(const mtg::WaypointParams, const mtg::TmemLaunch);  // + state in TMEM, staged output
+  void (*fn_tmem)(const mtg::WaypointParams, const mtg::TmemLaunch, const CUtensorMap);  // + TMEM state, TMA stores
   int stage_bytes_per_warp;
-  void (*fn_tmem_fused)(const mtg::WaypointParams, const mtg::TmemLaunch);  // + Nfabian times / packing fused
+  void (*fn_tmem_fused)(const mtg::WaypointParams, const mtg::TmemLaunch, const CUtensorMap);  // + fused Nfabian
 };
 #define MTG_WP(N_, R_, D_)                                                                   \
   {                                                                                          \
@@ -266,7 +266,7 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
         const int tslots = e->slots + e->D;  // TMEM kernel also keeps the vertex position in the state block
         const int ntm = cols ? std::min(nmax, cols / (2 * tslots)) : 0;
         if (cols && ntm == 0) continue;
-        const size_t smem = 16 + size_t(4) * e->stage_bytes_per_warp + size_t(2) * (1 + p->D) * mtg::kTmemThreads * 8 +
+        const size_t smem = mtg::kTmemHeaderBytes + size_t(4) * e->stage_bytes_per_warp + size_t(2) * (1 + p->D) * mtg::kTmemThreads * 8 +
                             size_t(nmax + 1) * mtg::kTmemThreads * 8 +
                             size_t(nmax - ntm) * tslots * mtg::kTmemThreads * sizeof(double);
         if (smem > h->smem_optin) continue;
@@ -297,8 +297,38 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
                                        (int)best_smem));
       const int64_t blocks = (B + 63) / 64;
       auto fn = fused ? e->fn_tmem_fused : e->fn_tmem;
+      // coeffs as a 2-D fp64 tensor [B][K*D*N] for the TMA stores (box = 16 trajectories x one segment)
+      CUtensorMap tmap;
+      {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        if (!encode) {
+          void* fp = nullptr;
+          cudaDriverEntryPointQueryResult qres;
+          MTG_CUDA(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres));
+          if (!fp || qres != cudaDriverEntryPointSuccess) {
+            h->error = "cuTensorMapEncodeTiled is not available from the driver";
+            return MTG_ERR_CUDA;
+          }
+          encode = reinterpret_cast<EncodeFn>(fp);
+        }
+        const cuuint64_t row = cuuint64_t(p->K) * p->D * p->N;
+        const cuuint64_t dims[2] = {row, cuuint64_t(B)};
+        const cuuint64_t strides[1] = {row * sizeof(double)};
+        const cuuint32_t box[2] = {cuuint32_t(p->D * p->N), 16u};
+        const cuuint32_t estr[2] = {1u, 1u};
+        const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, coeffs, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+          h->error = "cuTensorMapEncodeTiled failed (" + std::to_string(int(cr)) + ")";
+          return MTG_ERR_CUDA;
+        }
+      }
       MTG_CUDA(h, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem));
-      fn<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl);
+      fn<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl, tmap);
     } else if (use_v1) {
       MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v1));
       const int64_t blocks = (B + 31) / 32;

@@ -17,6 +17,8 @@
 // Mathematics, frames and index maps: see mtg_twisted_kernel.cuh.
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "mtg_twisted_kernel.cuh"
 
 namespace mtg {
@@ -140,10 +142,11 @@ struct TmemLaunch {
 };
 
 constexpr int kTmemThreads = 128;
+constexpr int kTmemHeaderBytes = 128;  // TMEM base-address holder, padded so that the staging tiles stay 128-B aligned
 
 template <int N, int D>
 __host__ __device__ constexpr int tmem_stage_bytes_per_warp() {
-  return 32 * (N / 2) * 16;  // one (segment, dimension) row of N doubles per lane
+  return 32 * D * (N / 2) * 16;  // one whole segment (D*N contiguous output doubles) per lane: two 16-row TMA boxes
 }
 
 template <int D>
@@ -155,10 +158,23 @@ __device__ __forceinline__ void cp_async8(const double* smem_dst, const double* 
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tmem::smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// TMA tensor store of a [16 rows][D*N doubles] shared-memory box to coeffs viewed as a 2-D tensor
+// [B trajectories][K*D*N doubles]: (c0 = first double inside the trajectory, c1 = first trajectory).  Rows
+// beyond the tensor (ragged last tile) are clipped by the hardware.
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tmap, const void* ssrc, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(tmem::smem_u32(ssrc)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int N, int R, int D, bool FUSED = false>
 __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
-    twisted_tmem_kernel(const WaypointParams prm, const TmemLaunch tl) {
+    twisted_tmem_kernel(const WaypointParams prm, const TmemLaunch tl, const __grid_constant__ CUtensorMap tmap) {
   constexpr int h = N / 2;
   constexpr int m = h - 1;
   constexpr int kL = m * (m + 1) / 2;
@@ -171,7 +187,7 @@ __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
   using G = H1Imm<N, R>;     // immediates: this kernel is register-bound (see mtg_device.cuh)
   using AI = A1InvImm<N>;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];  // TMA tensor stores need 128-byte aligned tiles
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int half = lane & 1;
@@ -183,15 +199,15 @@ __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
 
   // ---- shared memory carve-up: [holder 16 B][staging: kWarps tiles][spilled state]
   uint32_t* holder = reinterpret_cast<uint32_t*>(smem_raw);
-  double2* stage = reinterpret_cast<double2*>(smem_raw + 16) + size_t(warp) * 32 * h;
+  double2* stage = reinterpret_cast<double2*>(smem_raw + kTmemHeaderBytes) + size_t(warp) * 32 * (D * h);  // [half][16][D*h]
   // per-thread prefetch ring for the next step's inputs (segment time + D positions), filled by
   // cp.async: a register prefetch would share its scoreboard slot with the load being consumed and the
   // consumer would wait for the NEW loads as well (measured: 25 % of all stall samples).
-  double* pf = reinterpret_cast<double*>(smem_raw + 16 + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>()) + threadIdx.x;
+  double* pf = reinterpret_cast<double*>(smem_raw + kTmemHeaderBytes + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>()) + threadIdx.x;
   auto PF = [&](int buf, int slot) -> double* { return pf + (size_t(buf) * (1 + D) + slot) * kTmemThreads; };
   // per-thread history of the own-frame segment times seen by the inward sweep (nmax+1 doubles): the
   // outward sweep reads them back from shared memory (in FUSED mode this also saves the sqrt/exp)
-  double* thist = reinterpret_cast<double*>(smem_raw + 16 + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>() +
+  double* thist = reinterpret_cast<double*>(smem_raw + kTmemHeaderBytes + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>() +
                                             tmem_prefetch_bytes<D>()) +
                   threadIdx.x;
   auto HT = [&](int j) -> double& { return thist[size_t(j) * kTmemThreads]; };
@@ -283,22 +299,11 @@ __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
     tbase = *holder + (uint32_t(warp * 32) << 16);  // this warp's lane quarter
   }
 
-  // ---- per-lane constants of the cooperative store: piece e = it*32 + lane of the staging tile is
-  // 16 bytes c2 of row r (row r = lane r of this warp = trajectory r>>1, half r&1).
-  int st_off[h];      // double2 offset relative to the warp's first trajectory (segment/dimension added later)
-  int st_nh[h];       // eliminated-vertex count of the row's half (row active in step v iff v <= st_nh)
-  bool st_half[h], st_ok[h];
-#pragma unroll
-  for (int it = 0; it < h; ++it) {
-    const int e = it * 32 + lane;
-    const int r = e / h, c2 = e - r * h;
-    st_off[it] = (r >> 1) * (K * D * h) + c2;
-    st_half[it] = (r & 1) != 0;
-    st_nh[it] = (r & 1) ? K - M - 1 : M - 1;
-    st_ok[it] = traj0 + (r >> 1) < prm.B;
-  }
-  double2* __restrict__ out2 =
-      reinterpret_cast<double2*>(prm.coeffs) + (traj0 < prm.B ? traj0 : 0) * (long long)K * D * h;
+  // ---- output: each lane writes the D*N doubles of the segment it emits into row (half*16 + trajectory) of
+  // the warp's staging tile; one elected lane hands the two 16-row boxes (forward halves: segment j, reversed
+  // halves: segment K-1-j) to the TMA.  No cooperative read-back and no global-store LSU wavefronts.
+  double2* my_row = stage + ((lane & 1) * 16 + (lane >> 1)) * (D * h);
+  const int nhF = M - 1, nhB = K - M - 1;  // a half is active in sweep step v iff v <= its nh
 
   // emit own-frame segment j for every lane of the warp at once (convergent).  `act`: this lane's
   // values are meaningful; rows of inactive lanes are not stored.  v_step: the sweep step (0 = final).
@@ -312,7 +317,6 @@ __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
     itp[0] = pow_int<h>(iT);
 #pragma unroll
     for (int k = 1; k < h; ++k) itp[k] = itp[k - 1] * iT;
-    const int segF = j * (D * h), segB = (K - 1 - j) * (D * h);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       double c[N], ss[h], se[h];
@@ -345,15 +349,19 @@ __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
         for (int k = 1; k < h; ++k) acc = fma(AI::at(h + q, h + k), ee[k], acc);
         c[h + q] = acc * itp[q];
       }
-#pragma unroll
-      for (int q = 0; q < h; ++q) stage[lane * h + q] = make_double2(c[2 * q], c[2 * q + 1]);
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < h; ++it) {
-        const double2 val = stage[it * 32 + lane];
-        if (st_ok[it] && v_step <= st_nh[it]) out2[st_off[it] + (st_half[it] ? segB : segF) + d * h] = val;
+      if (d == 0) {  // the TMA must have finished reading the previous segment's tile
+        if (lane == 0) bulk_wait_read();
+        __syncwarp();
       }
-      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < h; ++q) my_row[d * h + q] = make_double2(c[2 * q], c[2 * q + 1]);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (v_step <= nhF) tma_store_box(&tmap, stage, j * (D * N), (int)traj0);
+      if (v_step <= nhB) tma_store_box(&tmap, stage + 16 * (D * h), (K - 1 - j) * (D * N), (int)traj0);
+      bulk_commit();
     }
   };
 
@@ -727,6 +735,7 @@ __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
     emit_all(0, 0, T, iT, sd, ed);
   }
 
+  if (lane == 0) bulk_wait_all();  // every TMA store issued by this warp has completed
   if (tl.tmem_cols > 0) {
     tmem::fence_before_sync();
     __syncthreads();
