@@ -9,10 +9,15 @@
 // per-thread LIFO.  A 128-thread CTA covers the 128 TMEM lanes; two CTAs per SM take 256 columns
 // each (128 doubles per thread); what does not fit spills to shared memory [vertex][slot][thread].
 //
-// Output: each lane writes the N coefficients of one (segment, dimension) to a per-warp staging
-// tile with 128-bit stores (row stride N*8 bytes: conflict free), then the warp streams the tile
-// out with 128-bit global stores in which consecutive lanes write consecutive 16-byte pieces
-// (runs of N*8 contiguous bytes) instead of 32 scattered 16-byte stores.
+// Output: each lane writes the D*N coefficients of the segment it has just solved into its row of a
+// 128-byte aligned per-warp staging tile ([half][16 trajectories][D*N doubles]); one elected lane then hands
+// the two 16-row boxes (forward halves: segment j, reversed halves: segment K-1-j) to the TMA with
+// cp.async.bulk.tensor.2d stores against a tensor map of coeffs viewed as [B][K*D*N].  No cooperative
+// read-back, no global-store LSU wavefronts, and the ragged last tile is clipped by the tensor map.
+//
+// Inputs: every lane prefetches the next step's segment time and waypoint with cp.async into a small
+// per-thread ring (a register prefetch would share its scoreboard slot with the value being consumed); the
+// outward sweep re-reads times from a per-thread shared-memory history and positions from the sweep state.
 //
 // Mathematics, frames and index maps: see mtg_twisted_kernel.cuh.
 #pragma once
