@@ -58,7 +58,7 @@ extern "C" {
 #define MTG_STATUS_NOT_SPD 2      /* non-positive / NaN pivot in the R_pp factorisation */
 
 /* which kernel family a problem is routed to (introspection for tests / profiles) */
-#define MTG_KERNEL_WAYPOINT 1     /* thread-per-trajectory block-tridiagonal Cholesky, waypoint topology */
+#define MTG_KERNEL_WAYPOINT 1     /* specialised block-tridiagonal Cholesky kernels, waypoint topology */
 #define MTG_KERNEL_GENERIC 2      /* arbitrary per-vertex masks, banded Cholesky in global scratch */
 #define MTG_KERNEL_NOFREE 3       /* n_free == 0: back-substitution only (linear_impl.h:343-349) */
 
@@ -96,7 +96,7 @@ int mtg_device_is_sm100(const mtg_handle* h);
 /* tuning knobs (results are identical to rounding; used by tests and profiles)
  *   MTG_OPT_WAYPOINT_VARIANT: 0 = default (= 3, falling back to 2 when the state does not fit),
  *                             1 = one thread per trajectory, 2 = twisted (state in shared memory),
- *                             3 = twisted with the sweep state in tensor memory + staged stores. */
+ *                             3 = twisted with the sweep state in tensor memory + TMA tensor stores. */
 #define MTG_OPT_WAYPOINT_VARIANT 1
 int mtg_set_option(mtg_handle* h, int key, int value);
 
