@@ -40,7 +40,7 @@
 // solve itself is "parity unpinned" by the reference; it is cross-checked instead against a
 // 60-digit mpmath solve of the same equations (oracle/truth.py).
 //
-// Build: see oracle/Makefile (g++ -O3 -march=native -shared -fPIC -pthread).
+// Build: see oracle/Makefile (g++ -O3 -march=x86-64-v3 -ffp-contract=off -shared -fPIC -pthread).
 
 #include <algorithm>
 #include <atomic>
