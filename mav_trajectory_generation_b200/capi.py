@@ -251,6 +251,16 @@ class Solver:
         self._check(rc, "mtg_solve_linear_batch_host_f64")
         return coeffs
 
+    def solve_waypoints_nfabian_host(self, N, r, positions, v_max, a_max, magic, coeffs, seg_times_out=None,
+                                     status=None):
+        """positions host [B][K+1][D] -> coeffs host [B][K][D][N] (pipelined H2D / fused solve / D2H)."""
+        B, K1, D = positions.shape
+        rc = self.lib.mtg_solve_waypoints_nfabian_batch_host_f64(
+            self.h, N, r, K1 - 1, D, B, self._hptr(positions), float(v_max), float(a_max), float(magic),
+            self._hptr(coeffs), self._hptr(seg_times_out), self._hptr(status))
+        self._check(rc, "mtg_solve_waypoints_nfabian_batch_host_f64")
+        return coeffs
+
     def coeffs_from_constraints_host(self, prob, seg_times, d_fixed, d_free, coeffs):
         B = seg_times.shape[0]
         rc = self.lib.mtg_coeffs_from_constraints_batch_host_f64(

@@ -44,12 +44,36 @@ struct mtg_handle {
   int64_t launches = 0;
   int waypoint_variant = 0;  // MTG_OPT_WAYPOINT_VARIANT
   std::vector<CachedTopology> topologies;
-  double* scratch = nullptr;
-  size_t scratch_bytes = 0;
-  double* pack_scratch = nullptr;  // times + d_fixed produced by nfabian_pack_kernel
-  size_t pack_scratch_bytes = 0;
   // host-pointer pipeline
   static constexpr int kPipe = 3;
+  // Scratch arenas are PER PIPELINE SLOT (index kPipe = launches on a caller-supplied stream): two chunks
+  // of the host pipeline run concurrently on different streams and must never share band / pack scratch.
+  // On the caller-stream slot consecutive users on DIFFERENT streams are ordered with an event.
+  struct Arena {
+    double* p = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t ev = nullptr;       // recorded after the last kernel that used the arena
+    cudaStream_t last = nullptr;
+    bool used = false;
+  };
+  Arena scratch[kPipe + 1];  // generic kernel: banded factor + right-hand sides
+  Arena pack[kPipe + 1];     // times + d_fixed produced by nfabian_pack_kernel; Mellinger expansion
+  // cached launch plans of the TMEM kernel (per waypoint entry and K): attributes are set once
+  struct TmemPlan {
+    const void* entry = nullptr;
+    int K = 0;
+    int cols = 0, ntm = 0, ctas = 0;
+    size_t smem = 0;
+    bool attr_plain = false, attr_fused = false;
+  };
+  std::vector<TmemPlan> plans;
+  // last encoded tensor map (B = 1 solveLinear() calls re-use the same output buffer)
+  struct TmapKey {
+    const void* base = nullptr;
+    int64_t B = 0;
+    int K = 0, D = 0, N = 0;
+  } tmap_key;
+  CUtensorMap tmap_cached;
   cudaStream_t streams[kPipe] = {nullptr, nullptr, nullptr};
   void* dev_buf[kPipe] = {nullptr, nullptr, nullptr};
   size_t dev_buf_bytes[kPipe] = {0, 0, 0};
@@ -197,17 +221,28 @@ CachedTopology* get_topology(mtg_handle* h, const mtg_problem* p) {
   return &h->topologies.back();
 }
 
-int ensure_scratch(mtg_handle* h, size_t bytes) {
-  if (bytes <= h->scratch_bytes) return MTG_OK;
-  // stream-ordered frees are not needed: scratch only grows and callers sync per handle
-  if (h->scratch) {
-    MTG_CUDA(h, cudaDeviceSynchronize());
-    cudaFree(h->scratch);
-    h->scratch = nullptr;
-    h->scratch_bytes = 0;
+// Grow-only arena.  acquire(): make the arena usable by a kernel about to be launched on `stream` (orders it
+// after the previous user when that one ran on another stream); release(): note the new last user.
+int arena_acquire(mtg_handle* h, mtg_handle::Arena& a, size_t bytes, cudaStream_t stream) {
+  if (bytes > a.bytes) {
+    if (a.p) {
+      MTG_CUDA(h, cudaDeviceSynchronize());
+      cudaFree(a.p);
+      a.p = nullptr;
+      a.bytes = 0;
+    }
+    MTG_CUDA(h, cudaMalloc(&a.p, bytes));
+    a.bytes = bytes;
+    a.used = false;
   }
-  MTG_CUDA(h, cudaMalloc(&h->scratch, bytes));
-  h->scratch_bytes = bytes;
+  if (a.used && a.last != stream) MTG_CUDA(h, cudaStreamWaitEvent(stream, a.ev, 0));
+  return MTG_OK;
+}
+int arena_release(mtg_handle* h, mtg_handle::Arena& a, cudaStream_t stream) {
+  if (!a.ev) MTG_CUDA(h, cudaEventCreateWithFlags(&a.ev, cudaEventDisableTiming));
+  MTG_CUDA(h, cudaEventRecord(a.ev, stream));
+  a.last = stream;
+  a.used = true;
   return MTG_OK;
 }
 
@@ -231,7 +266,8 @@ struct FusedInput {
 
 int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int64_t B, const double* times,
                  const double* dfix, const double* dfree_in, double* coeffs, double* dfree, int32_t* status,
-                 cudaStream_t stream, bool backsub_only, const FusedInput* fused = nullptr) {
+                 cudaStream_t stream, bool backsub_only, const FusedInput* fused = nullptr,
+                 int slot = mtg_handle::kPipe) {
   const Layout& L = topo->layout;
   if (B == 0) return MTG_OK;
   const int kind = backsub_only ? MTG_KERNEL_NOFREE : route(h, p, L);
@@ -253,35 +289,48 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
     prm.times_out = fused ? fused->times_out : nullptr;
     const size_t smem_v1 = size_t(p->K - 1) * e->slots * 32 * sizeof(double);
     const bool use_v1 = h->waypoint_variant == 1 && e->fn != nullptr && smem_v1 <= h->smem_optin;
-    if (h->waypoint_variant == 0 || h->waypoint_variant == 3 || fused) {
-      // Pick the TMEM column count / spill split that maximises resident CTAs per SM.
-      cudaFuncAttributes attr;
-      MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)e->fn_tmem));
+    // The TMA tensor stores need a 16-byte aligned output (cuTensorMapEncodeTiled); an 8-byte aligned
+    // caller buffer (e.g. a tensor slice) takes the shared-memory twisted kernel instead of failing.
+    const bool coeffs_aligned = (reinterpret_cast<uintptr_t>(coeffs) & 15u) == 0;
+    if ((h->waypoint_variant == 0 || h->waypoint_variant == 3 || fused) && (coeffs_aligned || fused)) {
+      if (!coeffs_aligned) return MTG_ERR_ALLOC;  // fused entry: caller falls back to pack + solve
       const int nmax = (p->K + 1) / 2 - 1;
-      const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
-      int best_ctas = 0, best_cols = 0, best_ntm = 0;
-      size_t best_smem = 0;
-      const int col_options[] = {512, 256, 128, 64, 32, 0};
-      for (int cols : col_options) {
-        const int tslots = e->slots + e->D;  // TMEM kernel also keeps the vertex position in the state block
-        const int ntm = cols ? std::min(nmax, cols / (2 * tslots)) : 0;
-        if (cols && ntm == 0) continue;
-        const size_t smem = mtg::kTmemHeaderBytes + size_t(4) * e->stage_bytes_per_warp + size_t(2) * (1 + p->D) * mtg::kTmemThreads * 8 +
-                            size_t(nmax + 1) * mtg::kTmemThreads * 8 +
-                            size_t(nmax - ntm) * tslots * mtg::kTmemThreads * sizeof(double);
-        if (smem > h->smem_optin) continue;
-        int ctas = std::min<int>(by_regs, int((228 * 1024) / (smem + 1024)));
-        ctas = std::min(ctas, 16);
-        if (cols) ctas = std::min(ctas, 512 / cols);
-        if (ctas > best_ctas || (ctas == best_ctas && smem < best_smem)) {
-          best_ctas = ctas;
-          best_cols = cols;
-          best_ntm = ntm;
-          best_smem = smem;
+      // ---- launch plan (TMEM column count / spill split maximising resident CTAs per SM): computed and
+      // the function attributes set ONCE per (kernel, K); a B = 1 solveLinear() call pays none of it again.
+      mtg_handle::TmemPlan* plan = nullptr;
+      for (auto& pl : h->plans)
+        if (pl.entry == (const void*)e && pl.K == p->K) plan = &pl;
+      if (!plan) {
+        cudaFuncAttributes attr;
+        MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)e->fn_tmem));
+        const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
+        mtg_handle::TmemPlan np;
+        np.entry = (const void*)e;
+        np.K = p->K;
+        const int col_options[] = {512, 256, 128, 64, 32, 0};
+        for (int cols : col_options) {
+          const int tslots = e->slots + e->D;  // TMEM kernel also keeps the vertex position in the state block
+          const int ntm = cols ? std::min(nmax, cols / (2 * tslots)) : 0;
+          if (cols && ntm == 0) continue;
+          const size_t smem = mtg::kTmemHeaderBytes + size_t(4) * e->stage_bytes_per_warp +
+                              size_t(2) * (1 + p->D) * mtg::kTmemThreads * 8 + size_t(nmax + 1) * mtg::kTmemThreads * 8 +
+                              size_t(nmax - ntm) * tslots * mtg::kTmemThreads * sizeof(double);
+          if (smem > h->smem_optin) continue;
+          int ctas = std::min<int>(by_regs, int((228 * 1024) / (smem + 1024)));
+          ctas = std::min(ctas, 16);
+          if (cols) ctas = std::min(ctas, 512 / cols);
+          if (ctas > np.ctas || (ctas == np.ctas && smem < np.smem)) {
+            np.ctas = ctas;
+            np.cols = cols;
+            np.ntm = ntm;
+            np.smem = smem;
+          }
         }
+        h->plans.push_back(np);
+        plan = &h->plans.back();
       }
-      if (best_ctas == 0 && fused) return MTG_ERR_ALLOC;  // caller falls back to pack + solve
-      if (best_ctas == 0) {  // sweep state too large for TMEM + shared memory of a 128-thread CTA
+      if (plan->ctas == 0 && fused) return MTG_ERR_ALLOC;  // caller falls back to pack + solve
+      if (plan->ctas == 0) {  // sweep state too large for TMEM + shared memory of a 128-thread CTA
         const size_t smem = size_t(nmax) * e->slots * 32 * sizeof(double);
         MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn_twisted, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
@@ -291,44 +340,55 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
         return MTG_OK;
       }
       mtg::TmemLaunch tl;
-      tl.n_tmem_blocks = best_ntm;
-      tl.tmem_cols = best_cols;
-      MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)best_smem));
+      tl.n_tmem_blocks = plan->ntm;
+      tl.tmem_cols = plan->cols;
       const int64_t blocks = (B + 63) / 64;
       auto fn = fused ? e->fn_tmem_fused : e->fn_tmem;
-      // coeffs as a 2-D fp64 tensor [B][K*D*N] for the TMA stores (box = 16 trajectories x one segment)
-      CUtensorMap tmap;
-      {
+      bool& attr_done = fused ? plan->attr_fused : plan->attr_plain;
+      if (!attr_done) {
+        MTG_CUDA(h, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
+        attr_done = true;
+      }
+      // coeffs as a 2-D fp64 tensor [B][K*D*N] for the TMA stores (box = 16 trajectories x one segment);
+      // the encoded map is cached for repeated calls on the same output buffer
+      if (!(h->tmap_key.base == coeffs && h->tmap_key.B == B && h->tmap_key.K == p->K && h->tmap_key.D == p->D &&
+            h->tmap_key.N == p->N)) {
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static EncodeFn encode = nullptr;
-        if (!encode) {
+        // function-local static with a lambda initialiser: initialised exactly once, thread-safe (C++11)
+        static const EncodeFn encode = []() -> EncodeFn {
           void* fp = nullptr;
           cudaDriverEntryPointQueryResult qres;
-          MTG_CUDA(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres));
-          if (!fp || qres != cudaDriverEntryPointSuccess) {
-            h->error = "cuTensorMapEncodeTiled is not available from the driver";
-            return MTG_ERR_CUDA;
-          }
-          encode = reinterpret_cast<EncodeFn>(fp);
+          if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess ||
+              qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+          return reinterpret_cast<EncodeFn>(fp);
+        }();
+        if (!encode) {
+          h->error = "cuTensorMapEncodeTiled is not available from the driver";
+          return MTG_ERR_CUDA;
         }
         const cuuint64_t row = cuuint64_t(p->K) * p->D * p->N;
         const cuuint64_t dims[2] = {row, cuuint64_t(B)};
         const cuuint64_t strides[1] = {row * sizeof(double)};
         const cuuint32_t box[2] = {cuuint32_t(p->D * p->N), 16u};
         const cuuint32_t estr[2] = {1u, 1u};
-        const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, coeffs, dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+        const CUresult cr = encode(&h->tmap_cached, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, coeffs, dims, strides, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) {
+          h->tmap_key.base = nullptr;
           h->error = "cuTensorMapEncodeTiled failed (" + std::to_string(int(cr)) + ")";
           return MTG_ERR_CUDA;
         }
+        h->tmap_key.base = coeffs;
+        h->tmap_key.B = B;
+        h->tmap_key.K = p->K;
+        h->tmap_key.D = p->D;
+        h->tmap_key.N = p->N;
       }
-      MTG_CUDA(h, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem));
-      fn<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl, tmap);
+      fn<<<(unsigned)blocks, mtg::kTmemThreads, plan->smem, stream>>>(prm, tl, h->tmap_cached);
     } else if (use_v1) {
       MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v1));
       const int64_t blocks = (B + 31) / 32;
@@ -375,11 +435,15 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
   } else {
     const size_t per_thread = size_t(L.n_free) * (L.bw + 1 + p->D);
     const size_t bytes = per_thread * size_t(blocks) * threads * sizeof(double);
-    const int rc = ensure_scratch(h, bytes);
+    mtg_handle::Arena& ar = h->scratch[slot];
+    int rc = arena_acquire(h, ar, bytes, stream);
     if (rc != MTG_OK) return rc;
-    prm.scratch = h->scratch;
+    prm.scratch = ar.p;
     prm.scratch_stride = blocks * threads;
     mtg::generic_solve_kernel<<<(unsigned)blocks, threads, 0, stream>>>(prm);
+    MTG_CUDA(h, cudaGetLastError());
+    rc = arena_release(h, ar, stream);
+    if (rc != MTG_OK) return rc;
   }
   MTG_CUDA(h, cudaGetLastError());
   h->launches++;
@@ -402,6 +466,9 @@ int ensure_pipe(mtg_handle* h, int i, size_t bytes) {
 }
 
 size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+// element counts of sub-buffers carved out of one allocation: keep every sub-buffer 256-byte aligned
+// (the TMA tensor map of the coefficient buffer needs >= 16 bytes)
+size_t align_doubles(size_t n) { return (n + 31) & ~size_t(31); }
 
 }  // namespace
 
@@ -448,8 +515,12 @@ void mtg_destroy(mtg_handle* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   for (auto& t : h->topologies) cudaFree(t.d_slot_col);
-  if (h->scratch) cudaFree(h->scratch);
-  if (h->pack_scratch) cudaFree(h->pack_scratch);
+  for (int i = 0; i <= mtg_handle::kPipe; ++i) {
+    for (mtg_handle::Arena* a : {&h->scratch[i], &h->pack[i]}) {
+      if (a->p) cudaFree(a->p);
+      if (a->ev) cudaEventDestroy(a->ev);
+    }
+  }
   for (int i = 0; i < mtg_handle::kPipe; ++i) {
     if (h->dev_buf[i]) cudaFree(h->dev_buf[i]);
     if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
@@ -503,9 +574,9 @@ int mtg_solve_linear_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, c
                       false);
 }
 
-int mtg_solve_waypoints_nfabian_batch_f64(mtg_handle* h, int32_t N, int32_t r, int32_t K, int32_t D, int64_t B,
-                                          const double* positions, double v_max, double a_max, double magic,
-                                          double* coeffs, double* seg_times_out, int32_t* status, void* stream) {
+static int nfabian_device(mtg_handle* h, int32_t N, int32_t r, int32_t K, int32_t D, int64_t B,
+                          const double* positions, double v_max, double a_max, double magic, double* coeffs,
+                          double* seg_times_out, int32_t* status, cudaStream_t s, int slot) {
   if (!h) return MTG_ERR_BAD_ARG;
   mtg_problem p = {N, r, K, D, nullptr};
   if (!valid_problem(&p) || B < 0 || !(v_max > 0.0) || !(a_max > 0.0) || (B > 0 && (!positions || !coeffs))) {
@@ -517,26 +588,18 @@ int mtg_solve_waypoints_nfabian_batch_f64(mtg_handle* h, int32_t N, int32_t r, i
   CachedTopology* topo = get_topology(h, &p);
   if (!topo) return MTG_ERR_CUDA;
   const Layout& L = topo->layout;
-  cudaStream_t s = (cudaStream_t)stream;
   if (route(h, &p, L) == MTG_KERNEL_WAYPOINT) {
     FusedInput f = {positions, v_max, a_max, magic, seg_times_out};
-    const int rc = launch_solve(h, &p, topo, B, nullptr, nullptr, nullptr, coeffs, nullptr, status, s, false, &f);
+    const int rc = launch_solve(h, &p, topo, B, nullptr, nullptr, nullptr, coeffs, nullptr, status, s, false, &f, slot);
     if (rc != MTG_ERR_ALLOC) return rc;
   }
   // no fused specialisation: pack (times, d_fixed) with a small kernel, then the regular path
-  const size_t n_t = size_t(B) * K, n_f = size_t(B) * D * L.n_fixed;
-  if ((n_t + n_f) * 8 > h->pack_scratch_bytes) {
-    if (h->pack_scratch) {
-      MTG_CUDA(h, cudaDeviceSynchronize());
-      cudaFree(h->pack_scratch);
-      h->pack_scratch = nullptr;
-      h->pack_scratch_bytes = 0;
-    }
-    MTG_CUDA(h, cudaMalloc(&h->pack_scratch, (n_t + n_f) * 8));
-    h->pack_scratch_bytes = (n_t + n_f) * 8;
-  }
-  double* t_buf = seg_times_out ? seg_times_out : h->pack_scratch;
-  double* f_buf = h->pack_scratch + n_t;
+  const size_t n_t = align_doubles(size_t(B) * K), n_f = size_t(B) * D * L.n_fixed;
+  mtg_handle::Arena& ar = h->pack[slot];
+  int rc = arena_acquire(h, ar, (n_t + n_f) * 8, s);
+  if (rc != MTG_OK) return rc;
+  double* t_buf = seg_times_out ? seg_times_out : ar.p;
+  double* f_buf = ar.p + n_t;
   mtg::PackParams pk;
   pk.N = N;
   pk.K = K;
@@ -554,7 +617,16 @@ int mtg_solve_waypoints_nfabian_batch_f64(mtg_handle* h, int32_t N, int32_t r, i
   mtg::nfabian_pack_kernel<<<(unsigned)blocks, threads, 0, s>>>(pk);
   MTG_CUDA(h, cudaGetLastError());
   h->launches++;
-  return launch_solve(h, &p, topo, B, t_buf, f_buf, nullptr, coeffs, nullptr, status, s, false);
+  rc = launch_solve(h, &p, topo, B, t_buf, f_buf, nullptr, coeffs, nullptr, status, s, false, nullptr, slot);
+  if (rc != MTG_OK) return rc;
+  return arena_release(h, ar, s);  // the solve was the last reader of the packed inputs
+}
+
+int mtg_solve_waypoints_nfabian_batch_f64(mtg_handle* h, int32_t N, int32_t r, int32_t K, int32_t D, int64_t B,
+                                          const double* positions, double v_max, double a_max, double magic,
+                                          double* coeffs, double* seg_times_out, int32_t* status, void* stream) {
+  return nfabian_device(h, N, r, K, D, B, positions, v_max, a_max, magic, coeffs, seg_times_out, status,
+                        (cudaStream_t)stream, mtg_handle::kPipe);
 }
 
 int mtg_coeffs_from_constraints_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B,
@@ -647,23 +719,20 @@ int mtg_cost_gradient_mellinger_batch_f64(mtg_handle* h, const mtg_problem* p, i
   const size_t per_x = (K + D * nf + K * D * N + 1) * 8;  // times + d_fixed + coeffs + cost of one expanded problem
   int64_t chunk = std::max<int64_t>(1, int64_t((size_t(384) << 20) / (per_x * (K + 1))));
   chunk = std::min<int64_t>(chunk, B);
-  const size_t need = per_x * (K + 1) * size_t(chunk);
-  if (need > h->pack_scratch_bytes) {
-    if (h->pack_scratch) {
-      MTG_CUDA(h, cudaDeviceSynchronize());
-      cudaFree(h->pack_scratch);
-      h->pack_scratch = nullptr;
-      h->pack_scratch_bytes = 0;
-    }
-    MTG_CUDA(h, cudaMalloc(&h->pack_scratch, need));
-    h->pack_scratch_bytes = need;
+  const size_t nx_max = size_t(chunk) * (K + 1);
+  const size_t o_f = align_doubles(nx_max * K), o_c = o_f + align_doubles(nx_max * D * nf),
+               o_j = o_c + align_doubles(nx_max * K * D * N), need = (o_j + align_doubles(nx_max)) * 8;
+  mtg_handle::Arena& ar = h->pack[mtg_handle::kPipe];
+  {
+    const int rc = arena_acquire(h, ar, need, s);
+    if (rc != MTG_OK) return rc;
   }
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
     const int64_t nb = std::min<int64_t>(chunk, B - b0), nx = nb * int64_t(K + 1);
-    double* t_x = h->pack_scratch;
-    double* f_x = t_x + size_t(nx) * K;
-    double* c_x = f_x + size_t(nx) * D * nf;
-    double* j_x = c_x + size_t(nx) * K * D * N;
+    double* t_x = ar.p;
+    double* f_x = ar.p + o_f;
+    double* c_x = ar.p + o_c;
+    double* j_x = ar.p + o_j;
     mtg::MellingerParams mp;
     mp.K = p->K;
     mp.D = p->D;
@@ -690,10 +759,20 @@ int mtg_cost_gradient_mellinger_batch_f64(mtg_handle* h, const mtg_problem* p, i
     MTG_CUDA(h, cudaGetLastError());
     h->launches++;
   }
-  return MTG_OK;
+  return arena_release(h, ar, s);
 }
 
 // ---- host-pointer variants: chunked H2D -> kernel -> D2H over kPipe streams ---------------
+// Every exit of a host-pointer entry point -- error returns included -- waits for all pipeline streams:
+// copies into caller-owned (possibly pinned) buffers must not be in flight when the caller gets control back.
+struct PipeSyncGuard {
+  mtg_handle* h;
+  ~PipeSyncGuard() {
+    for (int i = 0; i < mtg_handle::kPipe; ++i)
+      if (h->streams[i]) cudaStreamSynchronize(h->streams[i]);
+  }
+};
+
 static int host_pipeline(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
                          const double* d_fixed, const double* d_free_in, double* coeffs, double* d_free_out,
                          int32_t* status, bool backsub_only) {
@@ -720,6 +799,7 @@ static int host_pipeline(mtg_handle* h, const mtg_problem* p, int64_t B, const d
   if (B <= 4096) chunk = B;
   int rc = MTG_OK;
   int slot = 0;
+  PipeSyncGuard sync_on_exit{h};
   for (int64_t b0 = 0; b0 < B; b0 += chunk, slot = (slot + 1) % mtg_handle::kPipe) {
     const int64_t nb = std::min<int64_t>(chunk, B - b0);
     const size_t o_times = 0;
@@ -743,7 +823,7 @@ static int host_pipeline(mtg_handle* h, const mtg_problem* p, int64_t B, const d
                       need_free_in ? reinterpret_cast<double*>(base + o_freein) : nullptr,
                       reinterpret_cast<double*>(base + o_coef),
                       d_free_out ? reinterpret_cast<double*>(base + o_free) : nullptr,
-                      status ? reinterpret_cast<int32_t*>(base + o_stat) : nullptr, s, backsub_only);
+                      status ? reinterpret_cast<int32_t*>(base + o_stat) : nullptr, s, backsub_only, nullptr, slot);
     if (rc != MTG_OK) return rc;
     MTG_CUDA(h, cudaMemcpyAsync(coeffs + b0 * K * D * N, base + o_coef, b_coef * nb, cudaMemcpyDeviceToHost, s));
     if (d_free_out && L.n_free > 0)
@@ -779,6 +859,7 @@ int mtg_solve_waypoints_nfabian_batch_host_f64(mtg_handle* h, int32_t N, int32_t
   int64_t chunk = std::max<int64_t>(1, std::min<int64_t>((B + mtg_handle::kPipe - 1) / mtg_handle::kPipe, 32768));
   if (B <= 4096) chunk = B;
   int slot = 0;
+  PipeSyncGuard sync_on_exit{h};
   for (int64_t b0 = 0; b0 < B; b0 += chunk, slot = (slot + 1) % mtg_handle::kPipe) {
     const int64_t nb = std::min<int64_t>(chunk, B - b0);
     const size_t o_coef = align_up(b_pos * nb), o_t = align_up(o_coef + b_coef * nb), o_stat = align_up(o_t + b_t * nb);
@@ -787,10 +868,9 @@ int mtg_solve_waypoints_nfabian_batch_host_f64(mtg_handle* h, int32_t N, int32_t
     cudaStream_t s = h->streams[slot];
     char* base = static_cast<char*>(h->dev_buf[slot]);
     MTG_CUDA(h, cudaMemcpyAsync(base, positions + b0 * (K + 1) * D, b_pos * nb, cudaMemcpyHostToDevice, s));
-    rc = mtg_solve_waypoints_nfabian_batch_f64(h, N, r, K, D, nb, reinterpret_cast<double*>(base), v_max, a_max, magic,
-                                               reinterpret_cast<double*>(base + o_coef),
-                                               reinterpret_cast<double*>(base + o_t),
-                                               reinterpret_cast<int32_t*>(base + o_stat), s);
+    rc = nfabian_device(h, N, r, K, D, nb, reinterpret_cast<double*>(base), v_max, a_max, magic,
+                        reinterpret_cast<double*>(base + o_coef), reinterpret_cast<double*>(base + o_t),
+                        reinterpret_cast<int32_t*>(base + o_stat), s, slot);
     if (rc != MTG_OK) return rc;
     MTG_CUDA(h, cudaMemcpyAsync(coeffs + b0 * K * D * N, base + o_coef, b_coef * nb, cudaMemcpyDeviceToHost, s));
     if (seg_times_out)

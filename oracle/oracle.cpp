@@ -42,11 +42,15 @@
 //
 // Build: see oracle/Makefile (g++ -O3 -march=x86-64-v3 -ffp-contract=off -shared -fPIC -pthread).
 
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <random>
@@ -577,15 +581,21 @@ double oracle_solve_waypoint_batch(int N, int r, int K, int D, int64_t B, const 
   std::vector<std::thread> pool;
   std::vector<double> spent(n_threads, 0.0);
   std::atomic<int> failures{0};
+  std::atomic<int64_t> next_chunk{0};
+  constexpr int64_t kChunk = 64;
   const auto wall0 = std::chrono::steady_clock::now();
   for (int t = 0; t < n_threads; ++t) {
     pool.emplace_back([&, t]() {
       using clk = std::chrono::steady_clock;
-      const int64_t lo = B * t / n_threads, hi = B * (t + 1) / n_threads;
       std::vector<uint8_t> mask;
       std::vector<double> values;
       double acc = 0.0;
-      for (int64_t b = lo; b < hi; ++b) {
+      // dynamic chunks: on a shared host some threads get less CPU than others, and a static split would
+      // let the slowest one set the wall clock
+      for (;;) {
+       const int64_t lo = next_chunk.fetch_add(kChunk), hi = std::min<int64_t>(B, lo + kChunk);
+       if (lo >= B) break;
+       for (int64_t b = lo; b < hi; ++b) {
         const double* pos = positions + size_t(b) * (K + 1) * D;
         const double* tt = times + size_t(b) * K;
         waypoint_problem(N, K, D, pos, &mask, &values);
@@ -599,6 +609,7 @@ double oracle_solve_waypoint_batch(int N, int r, int K, int D, int64_t B, const 
         acc += std::chrono::duration<double>(t2 - (mode == 0 ? t0 : t1)).count();
         if (!ok) failures++;
         if (coeffs) std::memcpy(coeffs + size_t(b) * K * D * N, p.coeffs.data(), sizeof(double) * p.coeffs.size());
+       }
       }
       spent[t] = acc;
     });
@@ -650,6 +661,46 @@ int oracle_cost_gradient_mellinger(int N, int r, int K, int D, const double* pos
   return 0;
 }
 
-int oracle_hardware_threads() { return int(std::thread::hardware_concurrency()); }
+// Host threads this process can actually run concurrently: the scheduler affinity mask intersected with the
+// cgroup CPU quota (cgroup v2 cpu.max, v1 cpu.cfs_quota_us / cpu.cfs_period_us).  hardware_concurrency()
+// alone reports the machine, not the container.  info[0] = hardware_concurrency, [1] = affinity count,
+// [2] = cgroup quota in whole CPUs (0 = unlimited), [3] = effective.
+int oracle_cpu_info(int32_t* info) {
+  const int hw = int(std::thread::hardware_concurrency());
+  int aff = hw;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) aff = CPU_COUNT(&set);
+  int quota = 0;
+  {
+    double q = -1.0, per = 0.0;
+    if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+      char a[64] = {0};
+      if (std::fscanf(f, "%63s %lf", a, &per) == 2 && std::strcmp(a, "max") != 0) q = std::atof(a);
+      std::fclose(f);
+    } else {
+      if (FILE* f1 = std::fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {
+        if (std::fscanf(f1, "%lf", &q) != 1) q = -1.0;
+        std::fclose(f1);
+      }
+      if (FILE* f2 = std::fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) {
+        if (std::fscanf(f2, "%lf", &per) != 1) per = 0.0;
+        std::fclose(f2);
+      }
+    }
+    if (q > 0.0 && per > 0.0) quota = std::max(1, int(std::ceil(q / per)));
+  }
+  int eff = std::max(1, aff);
+  if (quota > 0) eff = std::min(eff, quota);
+  if (info) {
+    info[0] = hw;
+    info[1] = aff;
+    info[2] = quota;
+    info[3] = eff;
+  }
+  return eff;
+}
+
+int oracle_hardware_threads() { return oracle_cpu_info(nullptr); }
 
 }  // extern "C"

@@ -11,15 +11,21 @@ import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_ROOT, "oracle", "liboracle.so")
+_SO_EXACT = os.path.join(_ROOT, "oracle", "libexact.so")
 _lib = None
+_lib_exact = None
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
-    src = os.path.join(_ROOT, "oracle", "oracle.cpp")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    stale = force
+    for so, src in ((_SO, "oracle.cpp"), (_SO_EXACT, "exact.cpp")):
+        src = os.path.join(_ROOT, "oracle", src)
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            stale = True
+    if stale:
         subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "-s", "-B"])
     return _SO
 
@@ -48,8 +54,58 @@ def lib():
         L.oracle_cost_gradient_mellinger.restype = C.c_int
         L.oracle_cost_gradient_mellinger.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         L.oracle_hardware_threads.restype = C.c_int
+        L.oracle_cpu_info.restype = C.c_int
+        L.oracle_cpu_info.argtypes = [C.c_void_p]
         _lib = L
     return _lib
+
+
+def lib_exact():
+    global _lib_exact
+    if _lib_exact is None:
+        build()
+        L = C.CDLL(_SO_EXACT)
+        L.exact_solve_batch.restype = C.c_int
+        L.exact_solve_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, _dp, _dp, _dp,
+                                        C.c_void_p, C.c_void_p, C.c_int]
+        _lib_exact = L
+    return _lib_exact
+
+
+def exact_solve_batch(N, r, times, d_fixed, mask=None, n_threads=None, want_free=False, want_cost=False):
+    """binary128 solve (oracle/exact.cpp): times [B][K], d_fixed [B][D][n_fixed] (reference compact order) ->
+    coeffs [B][K][D][N] rounded once from ~34-digit arithmetic; with want_free / want_cost returns the tuple
+    (coeffs, d_free [B][D][n_free] or None, cost [B] or None)."""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    d_fixed = np.ascontiguousarray(d_fixed, dtype=np.float64)
+    B, K = times.shape
+    D = d_fixed.shape[1]
+    h = N // 2
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, dtype=np.uint8).reshape(K + 1, h)
+        n_fixed = int(mask.sum())
+    else:
+        n_fixed = 2 * h + K - 1
+    assert d_fixed.shape == (B, D, n_fixed), (d_fixed.shape, (B, D, n_fixed))
+    n_free = (K + 1) * h - n_fixed
+    coeffs = np.zeros((B, K, D, N))
+    dfree = np.zeros((B, D, max(n_free, 1))) if want_free else None
+    cost = np.zeros(B) if want_cost else None
+    rc = lib_exact().exact_solve_batch(N, r, K, D, mask.ctypes.data if mask is not None else None, B, times, d_fixed,
+                                       coeffs, dfree.ctypes.data if want_free else None,
+                                       cost.ctypes.data if want_cost else None, n_threads or hardware_threads())
+    if rc != 0:
+        raise RuntimeError(f"exact_solve_batch: rc={rc}")
+    if want_free or want_cost:
+        return coeffs, (dfree[:, :, :n_free] if want_free else None), cost
+    return coeffs
+
+
+def cpu_info():
+    """dict(hardware_concurrency, affinity, cgroup_quota_cpus (0 = unlimited), effective)."""
+    a = (C.c_int32 * 4)()
+    lib().oracle_cpu_info(C.addressof(a))
+    return dict(hardware_concurrency=a[0], affinity=a[1], cgroup_quota_cpus=a[2], effective=a[3])
 
 
 def solve(N, r, mask, values, times, want_cost=False):

@@ -8,7 +8,26 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-TOL = 1e-10
+TOL = 1e-10          # north_star: coefficients within 1e-10 (global-relative) of the reference path
+TOL_EXACT = 1e-12    # CUDA path vs the binary128 solve of the same equations (oracle/exact.cpp)
+BASELINE_SHAPES = {(10, 4, 16, 3), (10, 4, 8, 3), (8, 3, 4, 3), (10, 4, 2, 3)}   # C3, C2, C4, C1
+
+
+def check_parity(out, ref, exact, label, tol_exact=TOL_EXACT):
+    """The parity contract, per trajectory, with NO loosened tolerance:
+      (1) CUDA vs exact (binary128)            <= tol_exact (1e-12)
+      (2) CUDA vs oracle (reference-order fp64) <= 1e-10, and wherever that is exceeded the excursion must be
+          the oracle's own rounding: err(CUDA, oracle) <= err(oracle, exact) + 1e-12 on that same trajectory.
+    Returns the three per-trajectory error arrays."""
+    e_ge = global_rel_err(out, exact)
+    e_go = global_rel_err(out, ref)
+    e_oe = global_rel_err(ref, exact)
+    assert e_ge.max() <= tol_exact, f"{label}: CUDA vs exact {e_ge.max():.3e} (trajectory {int(e_ge.argmax())})"
+    bad = e_go > TOL
+    unexplained = bad & (e_go > e_oe + 1e-12)
+    assert not unexplained.any(), (f"{label}: CUDA vs oracle {e_go[unexplained].max():.3e} not explained by the "
+                                   f"oracle's own distance from exact {e_oe[unexplained].max():.3e}")
+    return e_ge, e_go, e_oe
 
 
 def global_rel_err(a, b):
@@ -35,6 +54,24 @@ def run_waypoint(solver, oracle, N, r, K, D, B, base_seed=1000, want_free=True, 
     torch.cuda.synchronize()
     solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, 0)
     return prob, pos, times, ref, out.cpu().numpy(), status.cpu().numpy(), (dfree.cpu().numpy() if want_free else None)
+
+
+@pytest.mark.parametrize("name,N,r,K,D", [("C3", 10, 4, 16, 3), ("C2", 10, 4, 8, 3), ("C4", 8, 3, 4, 3)])
+def test_baseline_configs_8192_fixtures_vs_exact_and_oracle(solver, oracle, name, N, r, K, D):
+    """>= 8192 bit-exact fixture trajectories (createRandomVertices seeds 1000+b, Nfabian v=3 a=5) for each
+    single-GPU BASELINE configuration, default kernel: CUDA vs binary128 <= 1e-12 on every trajectory, CUDA vs
+    the reference-order oracle <= 1e-10 except where the oracle itself is that far from exact (reference
+    LIN_impl.h:338-379 in fp64 loses ~5 digits on short segments; round 1 saw ONE C2 trajectory of 8192 at
+    1.08e-10 whose oracle-vs-exact distance is the same 1.08e-10)."""
+    B = 8192
+    prob, pos, times, ref, out, status, _ = run_waypoint(solver, oracle, N, r, K, D, B, want_free=False)
+    assert (status == 0).all()
+    exact = oracle.exact_solve_batch(N, r, times, oracle.waypoint_d_fixed(N, pos))
+    e_ge, e_go, e_oe = check_parity(out, ref, exact, name)
+    # the CUDA path is closer to exact than the reference-order arithmetic on (almost) every trajectory
+    assert np.median(e_ge) < np.median(e_oe)
+    print(f"{name}: CUDA-exact max {e_ge.max():.2e}  CUDA-oracle max {e_go.max():.2e} (#>1e-10: {(e_go > TOL).sum()})  "
+          f"oracle-exact max {e_oe.max():.2e}")
 
 
 @pytest.mark.parametrize("variant", [1, 2, 3])  # 1: thread per trajectory, 2: twisted, 3: twisted + TMEM state
@@ -69,13 +106,13 @@ def test_waypoint_kernel_matches_oracle(solver, oracle, N, r, K, D, B, variant):
             assert np.abs(got - want).max() <= 1e-9 * (1.0 + np.abs(want).max())
     assert prob.kernel == m.KERNEL_WAYPOINT
     assert (status == 0).all()
-    err = global_rel_err(out, ref)
-    # The 1e-10 bar is for the BASELINE fixtures (3-D, box +-10, v 3, a 5 => T >~ 3 s).  Elsewhere the
-    # reference-order arithmetic itself is further than 1e-10 from the exact answer (1-D fixtures have
-    # short segments, T ~ 1 s; r < N/2-1 cancels harder): there the oracle comparison is loose and
-    # test_gpu_vs_truth pins the kernel to the exact answer instead.
-    tol = TOL if ((N, r) in ((10, 4), (8, 3)) and D == 3) else (5e-9 if N < 12 else 1e-7)
-    assert err.max() <= tol, f"max global-relative error {err.max():.3e}"
+    # No loosened tolerance: the CUDA path is held to 1e-12 of the binary128 solve on every shape (N = 12
+    # included); against the reference-order oracle the bar is 1e-10 and an excursion must be explained by the
+    # oracle's own distance from exact on that same trajectory (1-D fixtures have T ~ 1 s segments, r < N/2-1
+    # cancels harder, N = 12 is worse still -- there the ORACLE is 1e-9..1e-7 from exact, the kernel is not).
+    exact = oracle.exact_solve_batch(N, r, times, oracle.waypoint_d_fixed(N, pos))
+    tol_exact = TOL_EXACT if (N, r, K, D) in BASELINE_SHAPES else 2e-12
+    check_parity(out, ref, exact, f"N={N} r={r} K={K} D={D} variant={variant}", tol_exact=tol_exact)
 
 
 def test_generic_kernel_matches_oracle_on_waypoint_mask(solver, oracle):
@@ -93,8 +130,8 @@ def test_generic_kernel_matches_oracle_on_waypoint_mask(solver, oracle):
     out = solver.solve_linear(prob, torch.from_numpy(times).cuda(), torch.from_numpy(dfix).cuda(), status=status)
     torch.cuda.synchronize()
     assert (status.cpu().numpy() == 0).all()
-    err = global_rel_err(out.cpu().numpy(), ref)
-    assert err.max() <= TOL, f"{err.max():.3e}"
+    exact = oracle.exact_solve_batch(N, r, times, dfix)
+    check_parity(out.cpu().numpy(), ref, exact, "K=100", tol_exact=2e-12)
 
 
 @pytest.mark.parametrize("N,r,K,D,seed", [(10, 4, 16, 3, 1000), (10, 4, 16, 1, 1003), (10, 3, 5, 3, 110), (10, 2, 5, 3, 109),
@@ -155,22 +192,16 @@ def test_generic_kernel_arbitrary_masks(solver, oracle):
                                   status=status)
         torch.cuda.synchronize()
         assert (status.cpu().numpy() == 0).all()
-        err = global_rel_err(out.cpu().numpy(), ref)
-        assert err.max() <= (5e-9 if N <= 10 else 1e-6), (trial, N, K, D, err.max())  # N=12: oracle's own rounding
-        # d_free against the oracle is loose (its QR works on the cancellation-prone A^-T Q A^-1; high free
-        # derivatives are poorly determined in that arithmetic) and tight against the 60-digit solve.
+        # every trajectory against the binary128 solve with the same mask; the oracle (whose QR works on the
+        # cancellation-prone A^-T Q A^-1) only has to be as close to the kernel as it is to exact
+        exact, exact_free, _ = oracle.exact_solve_batch(N, h - 1, times, dfix, mask=mask, want_free=True)
+        check_parity(out.cpu().numpy(), ref, exact, f"mask trial {trial} N={N} K={K} D={D}", tol_exact=1e-11)
         got_free = dfree.cpu().numpy()
-        rel = np.abs(got_free - dfree_ref).max() / np.abs(dfree_ref).max()
-        assert rel <= 1e-5, (trial, N, K, D, rel)
-        if trial < 4 or N == 12:
-            import os
-            import sys
-            sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
-            import truth
-            tru, tru_free = truth.solve(N, h - 1, mask, values[0], times[0])
-            e_c = np.abs(out.cpu().numpy()[0] - tru).max() / np.abs(tru).max()
-            e_f = np.abs(got_free[0] - tru_free).max() / np.abs(tru_free).max()
-            assert e_c <= 1e-11 and e_f <= 1e-10, (trial, N, K, D, e_c, e_f)
+        e_f = np.abs(got_free - exact_free).reshape(B, -1).max(axis=1) / np.abs(exact_free).reshape(B, -1).max(axis=1)
+        assert e_f.max() <= 1e-10, (trial, N, K, D, e_f.max())
+        e_of = np.abs(dfree_ref - exact_free).reshape(B, -1).max(axis=1) / np.abs(exact_free).reshape(B, -1).max(axis=1)
+        rel = np.abs(got_free - dfree_ref).reshape(B, -1).max(axis=1) / np.abs(dfree_ref).reshape(B, -1).max(axis=1)
+        assert (rel <= 1.01 * e_of + 1e-10).all(), (trial, N, K, D, rel.max(), e_of.max())
 
 
 def test_waypoint_nonzero_end_derivatives_and_dfree(solver, oracle):
@@ -346,8 +377,8 @@ def test_fused_nfabian_waypoint_entry(solver, oracle, N, r, K, D, B):
     assert (status.cpu().numpy() == 0).all()
     # device exp() vs glibc exp(): at most a couple of ulps apart
     np.testing.assert_allclose(t_out.cpu().numpy(), times, rtol=4e-16, atol=0)
-    tol = TOL if (N, r) in ((10, 4), (8, 3)) and D == 3 else 5e-9
-    assert global_rel_err(out.cpu().numpy(), ref).max() <= tol
+    exact = oracle.exact_solve_batch(N, r, times, oracle.waypoint_d_fixed(N, pos))
+    check_parity(out.cpu().numpy(), ref, exact, f"fused N={N} K={K} D={D}", tol_exact=2e-12)
 
 
 @pytest.mark.parametrize("N,r,K,D,B", [(10, 4, 16, 3, 40), (10, 4, 5, 3, 33), (8, 3, 4, 3, 50), (10, 4, 1, 3, 5)])
@@ -433,3 +464,91 @@ def test_small_orders_n2_n4(solver, oracle):
         torch.cuda.synchronize()
         assert (status.cpu().numpy() == 0).all(), (N, r)
         assert global_rel_err(out.cpu().numpy(), ref).max() <= 1e-11, (N, r)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Host-pointer pipeline: chunks run concurrently on 3 streams.  Round 1 shared ONE band / pack scratch between
+# them (a data race on generic topologies and on the Nfabian pack fallback).  These tests use PINNED buffers
+# (pageable copies serialise and hide the race) and B > one pipeline chunk.
+
+def _pinned(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+
+def test_host_pipeline_generic_mask_bitwise_equals_device_path(solver, oracle):
+    """Generic (non-waypoint) mask -- interior velocity fixed as well -- B = 100 003, pinned host buffers:
+    the pipelined host path must be bit-identical to one device-pointer launch, and correct vs exact."""
+    import torch
+    import mav_trajectory_generation_b200 as m
+    N, r, K, D, B = 10, 4, 6, 3, 100003
+    h = N // 2
+    mask = np.zeros((K + 1, h), dtype=np.uint8)
+    mask[:, 0] = 1
+    mask[:, 1] = 1          # velocity fixed at every vertex
+    mask[0, :] = 1
+    mask[-1, :] = 1
+    prob = m.Problem(N, r, K, D, fixed_mask=mask)
+    assert prob.kernel == m.KERNEL_GENERIC
+    rng = np.random.RandomState(3)
+    times = rng.uniform(2.0, 6.0, size=(B, K))
+    dfix = rng.uniform(-2, 2, size=(B, D, prob.n_fixed))
+    dev = solver.solve_linear(prob, torch.from_numpy(times).cuda(), torch.from_numpy(dfix).cuda())
+    torch.cuda.synchronize()
+    dev = dev.cpu().numpy()
+    for rep in range(2):
+        host = torch.zeros((B, K, D, N), dtype=torch.float64).pin_memory()
+        status = torch.full((B,), -1, dtype=torch.int32).pin_memory()
+        solver.solve_linear_host(prob, _pinned(times), _pinned(dfix), host, status=status)
+        assert bool((status == 0).all())
+        assert np.array_equal(host.numpy(), dev), f"host pipeline differs from the device path (rep {rep})"
+    sub = rng.choice(B, size=256, replace=False)
+    exact = oracle.exact_solve_batch(N, r, times[sub], dfix[sub], mask=mask)
+    assert global_rel_err(dev[sub], exact).max() <= 1e-11
+
+
+@pytest.mark.parametrize("N,r,K,D,B", [(10, 4, 6, 5, 20011), (10, 4, 100, 3, 6007)])
+def test_nfabian_host_pipeline_pack_fallback_bitwise(solver, oracle, N, r, K, D, B):
+    """mtg_solve_waypoints_nfabian_batch_host_f64 on shapes WITHOUT a fused kernel (D = 5; K = 100): pack kernel +
+    solve per chunk on 3 streams, B > 4096, pinned buffers -- bit-identical to one device-pointer call."""
+    import torch
+    rng = np.random.RandomState(8)
+    pos = rng.uniform(-10, 10, size=(B, K + 1, D))
+    dev_t = torch.zeros((B, K), dtype=torch.float64, device="cuda")
+    dev = solver.solve_waypoints_nfabian(N, r, torch.from_numpy(pos).cuda(), 3.0, 5.0, 6.5, seg_times_out=dev_t)
+    torch.cuda.synchronize()
+    host = torch.zeros((B, K, D, N), dtype=torch.float64).pin_memory()
+    host_t = torch.zeros((B, K), dtype=torch.float64).pin_memory()
+    status = torch.full((B,), -1, dtype=torch.int32).pin_memory()
+    solver.solve_waypoints_nfabian_host(N, r, _pinned(pos), 3.0, 5.0, 6.5, host, seg_times_out=host_t, status=status)
+    assert bool((status == 0).all())
+    assert np.array_equal(host_t.numpy(), dev_t.cpu().numpy())
+    assert np.array_equal(host.numpy(), dev.cpu().numpy())
+
+
+def test_mellinger_odd_offsets_and_unaligned_output(solver, oracle):
+    """(10,4,16,3) with B = 33 put the expanded coefficient buffer at an odd double offset (TMA
+    tensor maps need 16 bytes) -> MTG_ERR_CUDA.  Sub-buffers are now 256-byte aligned; and a caller buffer that
+    is only 8-byte aligned takes the shared-memory kernel instead of failing."""
+    import torch
+    import mav_trajectory_generation_b200 as m
+    N, r, K, D, B = 10, 4, 16, 3, 33
+    pos, times = oracle.make_waypoint_batch(K, D, B, base_seed=6100)
+    prob = m.Problem(N, r, K, D)
+    t_d = torch.from_numpy(times).cuda()
+    f_d = torch.from_numpy(oracle.waypoint_d_fixed(N, pos)).cuda()
+    cost, grad = solver.cost_gradient_mellinger(prob, t_d, f_d)
+    torch.cuda.synchronize()
+    c_ref, g_ref = oracle.cost_gradient_mellinger(N, r, pos[0], times[0])
+    assert abs(float(cost[0]) - c_ref) <= 1e-8 * abs(c_ref)
+    assert np.abs(grad[0].cpu().numpy() - g_ref).max() <= 1e-6 * max(abs(c_ref), np.abs(g_ref).max())
+    # 8-byte aligned output slice
+    aligned = solver.solve_linear(prob, t_d, f_d)
+    big = torch.zeros(B * K * D * N + 1, dtype=torch.float64, device="cuda")
+    odd = big[1:].view(B, K, D, N)
+    assert odd.data_ptr() % 16 == 8
+    solver.solve_linear(prob, t_d, f_d, coeffs=odd)
+    torch.cuda.synchronize()
+    exact = oracle.exact_solve_batch(N, r, times, oracle.waypoint_d_fixed(N, pos))
+    assert global_rel_err(odd.cpu().numpy(), exact).max() <= 2e-12
+    assert global_rel_err(aligned.cpu().numpy(), exact).max() <= 1e-12

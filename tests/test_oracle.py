@@ -191,3 +191,44 @@ def test_general_mask_vs_truth(oracle):
     tru, _ = truth.solve(N, 4, mask, values, times)
     assert np.abs(res["coeffs"] - tru).max() / np.abs(tru).max() <= 1e-9
     check_path(oracle, N, mask, values, times, res["coeffs"])
+
+
+@pytest.mark.parametrize("n_coeff,r,K,D,seed", [(10, 4, 16, 3, 1000), (10, 4, 8, 3, 1001), (8, 3, 4, 3, 1002), (12, 5, 6, 3, 3),
+                                               (10, 2, 5, 1, 107), (6, 2, 5, 3, 9)])
+def test_binary128_checker_vs_60_digit_truth(oracle, n_coeff, r, K, D, seed):
+    """oracle/exact.cpp (binary128, the checker the GPU suite uses at scale) rounds to the same fp64 numbers
+    as the 60-digit mpmath solve: <= 1 ulp of the largest coefficient, and its cost output agrees too."""
+    B = 2
+    pos, times = oracle.make_waypoint_batch(K, D, B, base_seed=seed)
+    dfix = oracle.waypoint_d_fixed(n_coeff, pos)
+    ex, ex_free, ex_cost = oracle.exact_solve_batch(n_coeff, r, times, dfix, n_threads=2, want_free=True, want_cost=True)
+    for b in range(B):
+        mask, values = oracle.waypoint_problem(n_coeff, pos[b])
+        tru, tru_free = truth.solve(n_coeff, r, mask, values, times[b])
+        assert np.abs(ex[b] - tru).max() <= 2.3e-16 * np.abs(tru).max()
+        if tru_free.size:
+            assert np.abs(ex_free[b] - tru_free).max() <= 2.3e-16 * np.abs(tru_free).max()
+        res = oracle.solve(n_coeff, r, mask, values, times[b])
+        assert abs(ex_cost[b] - res["cost"]) <= 1e-7 * abs(ex_cost[b])
+
+
+def test_binary128_checker_general_mask(oracle):
+    """Arbitrary masks (the generic kernel's checker): exact.cpp == truth.py to fp64 rounding."""
+    rng = np.random.RandomState(4)
+    n_coeff, K, D = 10, 4, 2
+    h = n_coeff // 2
+    mask = (rng.rand(K + 1, h) < 0.4).astype(np.uint8)
+    mask[:, 0] = 1
+    mask[0, :] = 1
+    values = rng.uniform(-2, 2, size=(K + 1, h, D)) * mask[:, :, None]
+    times = rng.uniform(2.0, 5.0, size=K)
+    res = oracle.solve(n_coeff, h - 1, mask, values, times)
+    ex = oracle.exact_solve_batch(n_coeff, h - 1, times[None], res["d_fixed"][None], mask=mask, n_threads=1)
+    tru, _ = truth.solve(n_coeff, h - 1, mask, values, times)
+    assert np.abs(ex[0] - tru).max() <= 2.3e-16 * np.abs(tru).max()
+
+
+def test_cpu_info_is_sane(oracle):
+    info = oracle.cpu_info()
+    assert 1 <= info["effective"] <= info["affinity"] <= max(info["hardware_concurrency"], info["affinity"])
+    assert oracle.hardware_threads() == info["effective"]
