@@ -2,12 +2,26 @@
 
 The batch is embarrassingly parallel (each trajectory is a closed problem; reference
 impl/polynomial_optimization_linear_impl.h:338-379 touches only its own members), so ranks own
-contiguous slices and the data path needs NO collective.  Collectives appear only when one rank
-holds the whole batch: `scatter_inputs` / `gather_outputs` move (seg_times, d_fixed) out and the
-coefficients back with NCCL (grouped send/recv under torch.distributed.scatter / gather; NVLink
-on a B200 box).  The same code runs on the gloo backend with CPU tensors, which is how the
-bookkeeping is tested without GPUs (tests/test_sharding_gloo.py).
+contiguous slices and the solve itself needs NO collective.  A collective appears only when one rank
+holds the whole batch (BASELINE.json config C5: "NCCL over NVLink only to scatter the vertex batch and
+gather the solved coefficients"): `scatter_solve_gather` below.
+
+Design of the exchange (NCCL has no native scatter/gather; these are grouped ncclSend/ncclRecv issued
+through torch.distributed.batch_isend_irecv):
+
+  * every rank's slice is cut into `chunks` pieces; step c of the pipeline is ONE NCCL group per rank that
+    carries the inputs of piece c root->rank AND the coefficients of piece c-1 rank->root, so the root's
+    NVLink egress (inputs) and ingress (coefficients) run full duplex and the solve of piece c overlaps
+    the gather of piece c-1;
+  * the root receives straight into slices of the preallocated [total][K][D][N] output (no staging
+    tensors, no torch.cat) and sends straight from slices of its input tensors;
+  * the root solves its own slice in place on its compute stream while the exchange progresses.
+
+The same code runs on the gloo backend with CPU tensors, which is how the bookkeeping is tested without
+GPUs (tests/test_sharding_gloo.py).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -17,49 +31,124 @@ def shard_bounds(total, world):
     return [total * r // world for r in range(world + 1)]
 
 
-def _padded(total, world):
-    return (total + world - 1) // world
+def chunk_bounds(lo, hi, chunks):
+    """Piece c of the slice [lo, hi) is [b[c], b[c+1])."""
+    n = hi - lo
+    return [lo + n * c // chunks for c in range(chunks + 1)]
 
 
-def scatter_inputs(times_root, dfix_root, total, K, D, n_fixed, device, src=0):
-    """Rank `src` passes the full [total][K] / [total][D][n_fixed] tensors (others pass None).
-    Returns this rank's (times, d_fixed, count) where count <= rows are meaningful."""
+def _wait_all(works):
+    for w in works:
+        w.wait()
+
+
+def scatter_solve_gather(solve_fn, times_root, dfix_root, out_root, total, K, D, N, n_fixed, device,
+                         root=0, chunks=4, local_buffers=None):
+    """BASELINE C5 data path.  On `root`: times_root [total][K], dfix_root [total][D][n_fixed] and the
+    preallocated out_root [total][K][D][N]; other ranks pass None for the three.  solve_fn(times, d_fixed,
+    coeffs) solves one contiguous piece into `coeffs` (asynchronously on the current stream).
+    Returns out_root on the root, None elsewhere.  `local_buffers` (non-root): dict reused across calls."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    per = _padded(total, world)
-    t_loc = torch.empty((per, K), dtype=torch.float64, device=device)
-    f_loc = torch.empty((per, D, n_fixed), dtype=torch.float64, device=device)
-    if rank == src:
-        pad = per * world - total
-        if pad:
-            # pad with copies of the last trajectory so every rank solves a well-posed problem
-            times_root = torch.cat([times_root, times_root[-1:].expand(pad, -1)])
-            dfix_root = torch.cat([dfix_root, dfix_root[-1:].expand(pad, -1, -1)])
-        t_list = [c.contiguous() for c in times_root.chunk(world)]
-        f_list = [c.contiguous() for c in dfix_root.chunk(world)]
-    else:
-        t_list = f_list = None
-    dist.scatter(t_loc, t_list, src=src)
-    dist.scatter(f_loc, f_list, src=src)
-    count = max(0, min(per, total - rank * per))
-    return t_loc, f_loc, count
+    bounds = shard_bounds(total, world)
+    if rank == root:
+        works = []
+        peers = [r for r in range(world) if r != root]
+        pieces = {r: chunk_bounds(bounds[r], bounds[r + 1], chunks) for r in peers}
+        for c in range(chunks + 1):
+            ops = []
+            for r in peers:
+                b = pieces[r]
+                if c < chunks and b[c + 1] > b[c]:
+                    ops.append(dist.P2POp(dist.isend, times_root[b[c]:b[c + 1]], r))
+                    ops.append(dist.P2POp(dist.isend, dfix_root[b[c]:b[c + 1]], r))
+                if c >= 1 and b[c] > b[c - 1]:
+                    ops.append(dist.P2POp(dist.irecv, out_root[b[c - 1]:b[c]], r))
+            if ops:
+                works += dist.batch_isend_irecv(ops)
+            if c == 0 and bounds[root + 1] > bounds[root]:
+                # the root's own slice: solved in place, concurrently with the exchange
+                lo, hi = bounds[root], bounds[root + 1]
+                solve_fn(times_root[lo:hi], dfix_root[lo:hi], out_root[lo:hi])
+        _wait_all(works)
+        return out_root
+    lo, hi = bounds[rank], bounds[rank + 1]
+    n = hi - lo
+    buf = local_buffers if local_buffers is not None else {}
+    if buf.get("n") != n or buf.get("shape") != (K, D, N, n_fixed):
+        buf["t"] = torch.empty((n, K), dtype=torch.float64, device=device)
+        buf["f"] = torch.empty((n, D, n_fixed), dtype=torch.float64, device=device)
+        buf["c"] = torch.empty((n, K, D, N), dtype=torch.float64, device=device)
+        buf["n"], buf["shape"] = n, (K, D, N, n_fixed)
+    b = [x - lo for x in chunk_bounds(lo, hi, chunks)]
+    works = []
+    for c in range(chunks + 1):
+        ops = []
+        if c < chunks and b[c + 1] > b[c]:
+            ops.append(dist.P2POp(dist.irecv, buf["t"][b[c]:b[c + 1]], root))
+            ops.append(dist.P2POp(dist.irecv, buf["f"][b[c]:b[c + 1]], root))
+        if c >= 1 and b[c] > b[c - 1]:
+            ops.append(dist.P2POp(dist.isend, buf["c"][b[c - 1]:b[c]], root))
+        if not ops:
+            continue
+        step = dist.batch_isend_irecv(ops)
+        if c < chunks and b[c + 1] > b[c]:
+            _wait_all(step)  # stream-ordered for NCCL: the solve below waits for piece c's inputs
+            solve_fn(buf["t"][b[c]:b[c + 1]], buf["f"][b[c]:b[c + 1]], buf["c"][b[c]:b[c + 1]])
+        else:
+            works += step
+    _wait_all(works)
+    return None
 
 
-def gather_outputs(coeffs_loc, total, dst=0):
-    """Inverse of scatter_inputs for the [per][K][D][N] coefficient tensors; returns the
-    [total][K][D][N] tensor on `dst` (None elsewhere)."""
-    world, rank = dist.get_world_size(), dist.get_rank()
-    if rank == dst:
-        parts = [torch.empty_like(coeffs_loc) for _ in range(world)]
-    else:
-        parts = None
-    dist.gather(coeffs_loc, parts, dst=dst)
-    if rank != dst:
+def solve_scattered(solve_fn, times_root, dfix_root, total, K, D, N, n_fixed, device, root=0, chunks=4):
+    """Convenience wrapper that allocates the output on the root (tests; bench.py preallocates)."""
+    out = None
+    if dist.get_rank() == root:
+        out = torch.empty((total, K, D, N), dtype=torch.float64, device=device)
+    return scatter_solve_gather(solve_fn, times_root, dfix_root, out, total, K, D, N, n_fixed, device, root=root,
+                                chunks=chunks)
+
+
+# ---- host side: NUMA placement of a rank's pinned buffers ------------------------------------------------
+
+def gpu_numa_node(index):
+    """NUMA node of CUDA device `index` from sysfs (None when unknown / single node)."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(path) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
         return None
-    return torch.cat(parts)[:total]
 
 
-def solve_scattered(solve_fn, times_root, dfix_root, total, K, D, N, n_fixed, device, root=0):
-    """scatter -> local solve -> gather.  solve_fn(times, d_fixed) -> coeffs [per][K][D][N]."""
-    t_loc, f_loc, _ = scatter_inputs(times_root, dfix_root, total, K, D, n_fixed, device, src=root)
-    c_loc = solve_fn(t_loc, f_loc)
-    return gather_outputs(c_loc, total, dst=root)
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(index):
+    """Restrict this process to the CPUs of the GPU's NUMA node, so that pinned host buffers allocated
+    afterwards are first-touched on that node and the H2D/D2H copies do not cross the inter-socket link.
+    Returns (node, previous affinity set) -- pass the set to os.sched_setaffinity(0, .) to undo -- or
+    (None, None) when nothing was changed."""
+    node = gpu_numa_node(index)
+    if node is None:
+        return None, None
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        prev = os.sched_getaffinity(0)
+        want = cpus & prev
+        if not want or want == prev:
+            return node, None
+        os.sched_setaffinity(0, want)
+        return node, prev
+    except Exception:
+        return None, None

@@ -22,12 +22,19 @@ def test_reference_arm_json_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert line["scaling"] == "strong" and line["config"]["total_trajectories"] == 1048576
+    # both arms print the same config dict (the driver's same_config check)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.config_dict("C5", 1048576)
+    cb = line["cpu_baseline"]
+    assert cb["cpu_info"]["effective"] >= cb["cores"] >= 1 and cb["per_core"] > 0
 
 
 @pytest.mark.gpu
 def test_gpu_arm_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3",
-                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+                          "--no-cpu-baseline", "--no-extras"], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert BASE_KEYS <= set(line)
@@ -39,3 +46,5 @@ def test_gpu_arm_json_line():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert e["bitwise_equal_to_device_path"]
     assert line["clocks"]["sm_mhz"] is not None
+    assert line["scaling"] == "strong" and line["config"]["total_trajectories"] == 1048576
+    assert line["shard"]["trajectories_per_gpu"] == 1048576

@@ -1,0 +1,8 @@
+#!/bin/bash
+# compute-sanitizer over tools/sanitize_target.py (every kernel family of the shipped library).
+out=${1:-gpurun_out/sanitizer.txt}
+: > "$out"
+for tool in memcheck racecheck synccheck; do
+  echo "=== compute-sanitizer --tool $tool (library $(sha1sum mav_trajectory_generation_b200/libmtg_b200.so | cut -c1-12)) ===" >> "$out"
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_target.py 2>&1 | grep -v "^$" | tail -25 >> "$out"
+done
