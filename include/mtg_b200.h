@@ -98,6 +98,10 @@ int mtg_device_is_sm100(const mtg_handle* h);
  *                             1 = one thread per trajectory, 2 = twisted (state in shared memory),
  *                             3 = twisted with the sweep state in tensor memory + TMA tensor stores. */
 #define MTG_OPT_WAYPOINT_VARIANT 1
+#define MTG_OPT_RING_DEPTH 2      /* persistent kernel: input ring buffers per thread, 2..4 */
+#define MTG_OPT_CTAS_PER_SM 3     /* persistent kernel: cap on resident CTAs per SM, 0 = as many as fit, 9 = one CTA per tile */
+#define MTG_OPT_STAGGER_US 4      /* persistent kernel: spread of the CTA start times, microseconds */
+#define MTG_OPT_DYNAMIC_TILES 5   /* persistent kernel: 1 = warps draw their tiles from a global counter */
 int mtg_set_option(mtg_handle* h, int key, int value);
 
 /* ---- host-only layout: the constraint reordering (linear_impl.h:181-260) ---------------- */
@@ -147,6 +151,23 @@ int mtg_cost_gradient_mellinger_batch_f64(mtg_handle* h, const mtg_problem* p, i
 int mtg_evaluate_batch_f64(mtg_handle* h, int32_t N, int32_t K, int32_t D, int64_t B, const double* seg_times,
                            const double* coeffs, int32_t derivative, double t_start, double dt, int32_t n_samples,
                            double* out, void* stream);
+
+/* batched Trajectory::evaluateRange (reference src/trajectory.cpp:81-141) -- and with
+ * derivs = {0,1,2,3,4} the sample set of sampleTrajectoryInRange (src/trajectory_sampling.cpp:45-110) -- for B
+ * trajectories at once.  The reference's sequential walk is replayed exactly (running time_in_segment += dt; the
+ * sample clock starts at the start of the segment that contains t_start; a sample on a segment end belongs to the
+ * left segment; the walk ends after the last segment), and every sample is Polynomial::evaluate's arithmetic
+ * (separate multiply and add), so samples are bit-identical to an x86 build of the reference.
+ *   out            [B][max_samples][n_derivs][D]   (rows >= n_samples[b] are zero)
+ *   n_samples      [B]  number of samples the reference would produce (may exceed max_samples: only the first
+ *                       max_samples are stored); -1 when t_start lies beyond the trajectory (reference: LOG(ERROR),
+ *                       empty result)
+ *   sampling_times [B][max_samples] or NULL: the reference's `sampling_times` output
+ * derivs is a HOST array of n_derivs (<= 8) derivative orders. */
+int mtg_evaluate_range_batch_f64(mtg_handle* h, int32_t N, int32_t K, int32_t D, int64_t B, const double* seg_times,
+                                 const double* coeffs, double t_start, double t_end, double dt, int32_t n_derivs,
+                                 const int32_t* derivs, int32_t max_samples, double* out, int32_t* n_samples,
+                                 double* sampling_times, void* stream);
 
 /* ---- the hot path, HOST pointers (what PolynomialOptimization<N>::solveLinear() calls) ---- */
 /* Same contract with host buffers; H2D, kernels and D2H are pipelined over internal streams and

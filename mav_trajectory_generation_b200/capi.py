@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "mtg_host_alloc", "mtg_host_free", "mtg_device_alloc", "mtg_device_free", "mtg_memcpy_h2d",
     "mtg_memcpy_d2h", "mtg_stream_synchronize", "mtg_version", "mtg_set_option",
     "mtg_solve_waypoints_nfabian_batch_f64", "mtg_solve_waypoints_nfabian_batch_host_f64",
-    "mtg_cost_gradient_mellinger_batch_f64", "mtg_evaluate_batch_f64",
+    "mtg_cost_gradient_mellinger_batch_f64", "mtg_evaluate_batch_f64", "mtg_evaluate_range_batch_f64",
 ]
 
 
@@ -80,6 +80,8 @@ def load():
     L.mtg_set_option.argtypes = [vp, C.c_int, C.c_int]
     L.mtg_evaluate_batch_f64.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i64, dp, dp, C.c_int32, C.c_double,
                                          C.c_double, C.c_int32, dp, vp]
+    L.mtg_evaluate_range_batch_f64.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i64, dp, dp, C.c_double, C.c_double,
+                                               C.c_double, C.c_int32, C.POINTER(C.c_int32), C.c_int32, dp, dp, dp, vp]
     L.mtg_cost_gradient_mellinger_batch_f64.argtypes = [vp, C.POINTER(MtgProblem), i64, dp, dp, dp, dp, vp]
     L.mtg_solve_waypoints_nfabian_batch_host_f64.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i64, dp,
                                                              C.c_double, C.c_double, C.c_double, dp, dp, dp]
@@ -196,6 +198,26 @@ class Solver:
                                              out.data_ptr(), s)
         self._check(rc, "mtg_evaluate_batch_f64")
         return out
+
+    def evaluate_range(self, seg_times, coeffs, t_start, t_end, dt, derivs=(0,), max_samples=None, want_times=False,
+                       stream=None):
+        """Batched Trajectory::evaluateRange: (out [B][S][len(derivs)][D], n_samples [B] int32, sampling_times or None)."""
+        import torch
+        B, K, D, N = coeffs.shape
+        if max_samples is None:
+            max_samples = int((t_end - t_start) / dt + 1) + 2
+        derivs = [int(x) for x in derivs]
+        arr = (C.c_int32 * len(derivs))(*derivs)
+        out = torch.empty((B, max_samples, len(derivs), D), dtype=torch.float64, device=coeffs.device)
+        n = torch.empty((B,), dtype=torch.int32, device=coeffs.device)
+        st = torch.zeros((B, max_samples), dtype=torch.float64, device=coeffs.device) if want_times else None
+        s = stream if stream is not None else torch.cuda.current_stream(coeffs.device).cuda_stream
+        rc = self.lib.mtg_evaluate_range_batch_f64(self.h, N, K, D, B, seg_times.data_ptr(), coeffs.data_ptr(),
+                                                   float(t_start), float(t_end), float(dt), len(derivs), arr,
+                                                   int(max_samples), out.data_ptr(), n.data_ptr(),
+                                                   st.data_ptr() if want_times else None, s)
+        self._check(rc, "mtg_evaluate_range_batch_f64")
+        return out, n, st
 
     def cost_gradient_mellinger(self, prob, seg_times, d_fixed, stream=None):
         """(cost [B], grad [B][K]) -- batched getCostAndGradientMellinger."""

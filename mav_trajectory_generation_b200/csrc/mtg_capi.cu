@@ -14,6 +14,7 @@
 #include "mtg_generic_kernel.cuh"
 #include "mtg_twisted_kernel.cuh"
 #include "mtg_twisted_tmem_kernel.cuh"
+#include "mtg_twisted_tmem_v4_kernel.cuh"
 #include "mtg_waypoint_kernel.cuh"
 
 namespace {
@@ -43,6 +44,11 @@ struct mtg_handle {
   std::string error;
   int64_t launches = 0;
   int waypoint_variant = 0;  // MTG_OPT_WAYPOINT_VARIANT
+  int ring_depth = 3;        // MTG_OPT_RING_DEPTH (v4 kernel: cp.async input ring buffers, 2..4)
+  int ctas_per_sm = 0;       // MTG_OPT_CTAS_PER_SM (v4 kernel: 0 = as many as fit, 9 = one CTA per tile, not persistent)
+  int stagger_us = 0;        // MTG_OPT_STAGGER_US (v4 kernel: CTA start times spread over this many microseconds)
+  int dynamic_tiles = 0;     // MTG_OPT_DYNAMIC_TILES (v4 kernel: warps draw tiles from a global counter)
+  unsigned long long* tile_counters = nullptr;  // one per pipeline slot (+ caller stream)
   std::vector<CachedTopology> topologies;
   // host-pointer pipeline
   static constexpr int kPipe = 3;
@@ -182,6 +188,29 @@ const WaypointEntry kWaypointKernels[] = {
     MTG_WP2(6, 2, 3),  MTG_WP2(6, 2, 1),                                          // min acceleration, N = 6
 };
 
+// ---- v4 (persistent) kernels: instantiated for the BASELINE shapes
+typedef void (*V4Kernel)(const mtg::WaypointParams, const mtg::TmemLaunchV4, const CUtensorMap);
+struct V4Entry {
+  int N, R, D;
+  V4Kernel fn[3];        // ring depth 2, 3, 4
+  V4Kernel fn_fused[3];
+};
+#define MTG_V4(N_, R_, D_, MB_)                                                                               \
+  {                                                                                                           \
+    N_, R_, D_,                                                                                               \
+        {mtg::twisted_tmem_v4_kernel<N_, R_, D_, false, 2, MB_>, mtg::twisted_tmem_v4_kernel<N_, R_, D_, false, 3, MB_>, \
+         mtg::twisted_tmem_v4_kernel<N_, R_, D_, false, 4, MB_>},                                             \
+        {mtg::twisted_tmem_v4_kernel<N_, R_, D_, true, 2, MB_>, mtg::twisted_tmem_v4_kernel<N_, R_, D_, true, 3, MB_>,   \
+         mtg::twisted_tmem_v4_kernel<N_, R_, D_, true, 4, MB_>}                                               \
+  }
+const V4Entry kV4Kernels[] = {MTG_V4(10, 4, 3, 2), MTG_V4(8, 3, 3, 3)};
+
+const V4Entry* find_v4(const mtg_problem* p) {
+  for (const auto& e : kV4Kernels)
+    if (e.N == p->N && e.R == p->r && e.D == p->D) return &e;
+  return nullptr;
+}
+
 const WaypointEntry* find_waypoint(const mtg_handle* h, const mtg_problem* p, const Layout& L) {
   if (!L.waypoint) return nullptr;
   for (const auto& e : kWaypointKernels)
@@ -258,6 +287,39 @@ struct DeviceGuard {
   }
 };
 
+// coeffs as a 2-D fp64 tensor [B][K*D*N] for the TMA stores (box = 16 trajectories x one segment)
+int encode_coeff_tmap(mtg_handle* h, CUtensorMap* out, double* coeffs, int64_t B, const mtg_problem* p) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  // function-local static with a lambda initialiser: initialised exactly once, thread-safe (C++11)
+  static const EncodeFn encode = []() -> EncodeFn {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeFn>(fp);
+  }();
+  if (!encode) {
+    h->error = "cuTensorMapEncodeTiled is not available from the driver";
+    return MTG_ERR_CUDA;
+  }
+  const cuuint64_t row = cuuint64_t(p->K) * p->D * p->N;
+  const cuuint64_t dims[2] = {row, cuuint64_t(B)};
+  const cuuint64_t strides[1] = {row * sizeof(double)};
+  const cuuint32_t box[2] = {cuuint32_t(p->D * p->N), 16u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult cr = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, coeffs, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    h->error = "cuTensorMapEncodeTiled failed (" + std::to_string(int(cr)) + ")";
+    return MTG_ERR_CUDA;
+  }
+  return MTG_OK;
+}
+
 struct FusedInput {
   const double* positions;
   double v_max, a_max, magic;
@@ -270,6 +332,9 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
                  int slot = mtg_handle::kPipe) {
   const Layout& L = topo->layout;
   if (B == 0) return MTG_OK;
+  // clear a stale (non-sticky) error another library of the process may have left behind: the
+  // cudaGetLastError() after our launches must report OUR launch only
+  (void)cudaGetLastError();
   const int kind = backsub_only ? MTG_KERNEL_NOFREE : route(h, p, L);
   if (kind == MTG_KERNEL_WAYPOINT) {
     const WaypointEntry* e = find_waypoint(h, p, L);
@@ -292,6 +357,66 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
     // The TMA tensor stores need a 16-byte aligned output (cuTensorMapEncodeTiled); an 8-byte aligned
     // caller buffer (e.g. a tensor slice) takes the shared-memory twisted kernel instead of failing.
     const bool coeffs_aligned = (reinterpret_cast<uintptr_t>(coeffs) & 15u) == 0;
+    if (h->waypoint_variant == 4 && coeffs_aligned) {
+      const V4Entry* e4 = find_v4(p);
+      if (e4) {
+        const int rd = h->ring_depth;
+        V4Kernel fn = (fused ? e4->fn_fused : e4->fn)[rd - 2];
+        const int hh = p->N / 2, mm = hh - 1;
+        const int kslots = mm * (mm + 1) / 2 + mm * p->D + p->D, kpro = 2 * p->D + mm * p->D + 1;
+        const int nmax = (p->K + 1) / 2 - 1;
+        cudaFuncAttributes attr;
+        MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)fn));
+        const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
+        int best_ctas = 0, best_cols = 0, best_ntm = 0;
+        size_t best_smem = 0;
+        const int col_options[] = {512, 256, 128, 64, 32, 0};
+        for (int cols : col_options) {
+          const int ntm = cols ? std::min(nmax, cols / (2 * kslots)) : 0;
+          if (cols && ntm == 0 && nmax > 0) continue;
+          const int spill = std::max(0, nmax - ntm) * kslots;
+          const size_t smem = mtg::kTmemHeaderBytes + size_t(4) * e->stage_bytes_per_warp +
+                              size_t(rd * (1 + p->D) + (nmax + 1) + p->D + std::max(spill, kpro)) * mtg::kTmemThreads * 8;
+          if (smem > h->smem_optin) continue;
+          int ctas = std::min<int>(by_regs, int((228 * 1024) / (smem + 1024)));
+          if (cols) ctas = std::min(ctas, 512 / cols);
+          ctas = std::min(ctas, 8);
+          if (ctas > best_ctas || (ctas == best_ctas && smem < best_smem)) {
+            best_ctas = ctas;
+            best_cols = cols;
+            best_ntm = ntm;
+            best_smem = smem;
+          }
+        }
+        if (best_ctas > 0) {
+          const bool per_tile = h->ctas_per_sm == 9;
+          if (h->ctas_per_sm > 0 && !per_tile) best_ctas = std::min(best_ctas, h->ctas_per_sm);
+          mtg::TmemLaunchV4 tl;
+          tl.n_tmem_blocks = best_ntm;
+          tl.tmem_cols = best_cols;
+          tl.region_slots = 0;
+          tl.tile_counter = nullptr;
+          tl.stagger_ns = per_tile ? 0u : unsigned(h->stagger_us) * 1000u;
+          if (h->dynamic_tiles && !per_tile) {
+            if (!h->tile_counters) MTG_CUDA(h, cudaMalloc(&h->tile_counters, sizeof(unsigned long long) * 32 * (mtg_handle::kPipe + 1)));
+            tl.tile_counter = h->tile_counters + 32 * slot;  // 256-byte apart
+            MTG_CUDA(h, cudaMemsetAsync(tl.tile_counter, 0, sizeof(unsigned long long), stream));
+          }
+          MTG_CUDA(h, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem));
+          CUtensorMap tmap;
+          {
+            const int rc = encode_coeff_tmap(h, &tmap, coeffs, B, p);
+            if (rc != MTG_OK) return rc;
+          }
+          const int64_t ctiles = (B + 63) / 64;
+          const int64_t blocks = per_tile ? ctiles : std::min<int64_t>(ctiles, int64_t(best_ctas) * h->sm_count);
+          fn<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl, tmap);
+          MTG_CUDA(h, cudaGetLastError());
+          h->launches++;
+          return MTG_OK;
+        }
+      }
+    }
     if ((h->waypoint_variant == 0 || h->waypoint_variant == 3 || fused) && (coeffs_aligned || fused)) {
       if (!coeffs_aligned) return MTG_ERR_ALLOC;  // fused entry: caller falls back to pack + solve
       const int nmax = (p->K + 1) / 2 - 1;
@@ -353,34 +478,10 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
       // the encoded map is cached for repeated calls on the same output buffer
       if (!(h->tmap_key.base == coeffs && h->tmap_key.B == B && h->tmap_key.K == p->K && h->tmap_key.D == p->D &&
             h->tmap_key.N == p->N)) {
-        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        // function-local static with a lambda initialiser: initialised exactly once, thread-safe (C++11)
-        static const EncodeFn encode = []() -> EncodeFn {
-          void* fp = nullptr;
-          cudaDriverEntryPointQueryResult qres;
-          if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess ||
-              qres != cudaDriverEntryPointSuccess)
-            return nullptr;
-          return reinterpret_cast<EncodeFn>(fp);
-        }();
-        if (!encode) {
-          h->error = "cuTensorMapEncodeTiled is not available from the driver";
-          return MTG_ERR_CUDA;
-        }
-        const cuuint64_t row = cuuint64_t(p->K) * p->D * p->N;
-        const cuuint64_t dims[2] = {row, cuuint64_t(B)};
-        const cuuint64_t strides[1] = {row * sizeof(double)};
-        const cuuint32_t box[2] = {cuuint32_t(p->D * p->N), 16u};
-        const cuuint32_t estr[2] = {1u, 1u};
-        const CUresult cr = encode(&h->tmap_cached, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, coeffs, dims, strides, box,
-                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) {
+        const int rc = encode_coeff_tmap(h, &h->tmap_cached, coeffs, B, p);
+        if (rc != MTG_OK) {
           h->tmap_key.base = nullptr;
-          h->error = "cuTensorMapEncodeTiled failed (" + std::to_string(int(cr)) + ")";
-          return MTG_ERR_CUDA;
+          return rc;
         }
         h->tmap_key.base = coeffs;
         h->tmap_key.B = B;
@@ -515,6 +616,7 @@ void mtg_destroy(mtg_handle* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   for (auto& t : h->topologies) cudaFree(t.d_slot_col);
+  if (h->tile_counters) cudaFree(h->tile_counters);
   for (int i = 0; i <= mtg_handle::kPipe; ++i) {
     for (mtg_handle::Arena* a : {&h->scratch[i], &h->pack[i]}) {
       if (a->p) cudaFree(a->p);
@@ -536,8 +638,24 @@ int mtg_device_is_sm100(const mtg_handle* h) { return h && h->cc_major == 10; }
 
 int mtg_set_option(mtg_handle* h, int key, int value) {
   if (!h) return MTG_ERR_BAD_ARG;
-  if (key == MTG_OPT_WAYPOINT_VARIANT && value >= 0 && value <= 3) {
+  if (key == MTG_OPT_WAYPOINT_VARIANT && value >= 0 && value <= 4) {
     h->waypoint_variant = value;
+    return MTG_OK;
+  }
+  if (key == MTG_OPT_RING_DEPTH && value >= 2 && value <= 4) {
+    h->ring_depth = value;
+    return MTG_OK;
+  }
+  if (key == MTG_OPT_CTAS_PER_SM && value >= 0 && value <= 9) {
+    h->ctas_per_sm = value;
+    return MTG_OK;
+  }
+  if (key == MTG_OPT_STAGGER_US && value >= 0 && value <= 1000) {
+    h->stagger_us = value;
+    return MTG_OK;
+  }
+  if (key == MTG_OPT_DYNAMIC_TILES && (value == 0 || value == 1)) {
+    h->dynamic_tiles = value;
     return MTG_OK;
   }
   h->error = "unknown option";
@@ -700,6 +818,65 @@ int mtg_evaluate_batch_f64(mtg_handle* h, int32_t N, int32_t K, int32_t D, int64
   MTG_CUDA(h, cudaGetLastError());
   h->launches++;
   return MTG_OK;
+}
+
+int mtg_evaluate_range_batch_f64(mtg_handle* h, int32_t N, int32_t K, int32_t D, int64_t B, const double* seg_times,
+                                 const double* coeffs, double t_start, double t_end, double dt, int32_t n_derivs,
+                                 const int32_t* derivs, int32_t max_samples, double* out, int32_t* n_samples,
+                                 double* sampling_times, void* stream) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  if (N < 1 || N > MTG_MAX_N || K < 1 || D < 1 || B < 0 || n_derivs < 1 || n_derivs > 8 || !derivs || max_samples < 0 ||
+      !(dt > 0.0) || (B > 0 && (!seg_times || !coeffs || !n_samples || (max_samples > 0 && !out)))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  for (int q = 0; q < n_derivs; ++q)
+    if (derivs[q] < 0) {
+      h->error = "bad argument";
+      return MTG_ERR_BAD_ARG;
+    }
+  if (B == 0) return MTG_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t ns = size_t(B) * size_t(std::max(max_samples, 1));
+  mtg_handle::Arena& ar = h->pack[mtg_handle::kPipe];
+  const size_t o_idx = align_doubles(ns);  // t_local first (doubles), then seg_idx (int32)
+  int rc = arena_acquire(h, ar, (o_idx + align_doubles((ns + 1) / 2)) * 8, s);
+  if (rc != MTG_OK) return rc;
+  mtg::RangeParams rp;
+  rp.N = N;
+  rp.K = K;
+  rp.D = D;
+  rp.n_derivs = n_derivs;
+  rp.max_samples = max_samples;
+  for (int q = 0; q < 8; ++q) rp.derivs[q] = q < n_derivs ? derivs[q] : 0;
+  rp.B = B;
+  rp.t_start = t_start;
+  rp.t_end = t_end;
+  rp.dt = dt;
+  rp.times = seg_times;
+  rp.coeffs = coeffs;
+  rp.t_local = ar.p;
+  rp.seg_idx = reinterpret_cast<int*>(ar.p + o_idx);
+  rp.n_samples = n_samples;
+  rp.sampling_times = sampling_times;
+  rp.out = out;
+  {
+    const int threads = 128;
+    const int64_t blocks = std::min<int64_t>((B + threads - 1) / threads, int64_t(h->sm_count) * 16);
+    mtg::range_walk_kernel<<<(unsigned)blocks, threads, 0, s>>>(rp);
+    MTG_CUDA(h, cudaGetLastError());
+    h->launches++;
+  }
+  if (max_samples > 0) {
+    const int threads = 256;
+    const int64_t total = B * int64_t(max_samples);
+    const int64_t blocks = std::min<int64_t>((total + threads - 1) / threads, int64_t(h->sm_count) * 32);
+    mtg::range_eval_kernel<<<(unsigned)blocks, threads, 0, s>>>(rp);
+    MTG_CUDA(h, cudaGetLastError());
+    h->launches++;
+  }
+  return arena_release(h, ar, s);
 }
 
 int mtg_cost_gradient_mellinger_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,

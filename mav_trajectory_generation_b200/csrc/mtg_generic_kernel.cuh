@@ -345,6 +345,111 @@ __global__ void __launch_bounds__(256) evaluate_kernel(const EvalParams prm) {
   }
 }
 
+// Batched Trajectory::evaluateRange (reference src/trajectory.cpp:81-141) / sampleTrajectoryInRange
+// (src/trajectory_sampling.cpp:45-110).  The reference walks the segments SEQUENTIALLY with a running
+// `time_in_segment += dt` / `accumulated_time += dt` (so sample k is not t_start + k*dt in floating point, the
+// sample clock starts at the start of the segment containing t_start, and a sample exactly on a segment end
+// belongs to the left segment).  Phase 1 replays that walk, one thread per trajectory, and records for every
+// sample its segment and local time; phase 2 evaluates all requested derivative orders of all dimensions, one
+// thread per (trajectory, sample), with Polynomial::evaluate's own arithmetic (polynomial.h:134-149: Horner
+// with a separate multiply and add -- no FMA contraction, so the samples are bit-identical to an x86 build of
+// the reference).
+struct RangeParams {
+  int N, K, D, n_derivs, max_samples;
+  int derivs[8];
+  long long B;
+  double t_start, t_end, dt;
+  const double* __restrict__ times;    // [B][K]
+  const double* __restrict__ coeffs;   // [B][K][D][N]
+  int* __restrict__ seg_idx;           // [B][max_samples] scratch
+  double* __restrict__ t_local;        // [B][max_samples] scratch
+  int* __restrict__ n_samples;         // [B]; -1: t_start beyond the trajectory (reference logs an error, no samples)
+  double* __restrict__ sampling_times; // [B][max_samples] or null
+  double* __restrict__ out;            // [B][max_samples][n_derivs][D]
+};
+
+__global__ void __launch_bounds__(128) range_walk_kernel(const RangeParams prm) {
+  const int K = prm.K, S = prm.max_samples;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < prm.B; b += nthreads) {
+    const double* __restrict__ tt = prm.times + b * K;
+    int* __restrict__ si = prm.seg_idx + b * S;
+    double* __restrict__ tl = prm.t_local + b * S;
+    double* __restrict__ st = prm.sampling_times ? prm.sampling_times + b * S : nullptr;
+    double accumulated = 0.0;
+    int i = 0;
+    for (i = 0; i < K; ++i) {
+      accumulated = __dadd_rn(accumulated, tt[i]);
+      if (accumulated > prm.t_start) break;
+    }
+    if (prm.t_start > accumulated) {
+      prm.n_samples[b] = -1;
+      continue;
+    }
+    int n = 0;
+    if (i < K) {
+      double Ti = tt[i];
+      accumulated = __dsub_rn(accumulated, Ti);
+      double tis = __dsub_rn(prm.t_start, accumulated);
+      while (accumulated < prm.t_end) {
+        if (tis > Ti) {
+          tis = __dsub_rn(tis, Ti);
+          ++i;
+          if (i >= K) break;
+          Ti = tt[i];
+          continue;
+        }
+        if (n < S) {
+          si[n] = i;
+          tl[n] = tis;
+          if (st) st[n] = accumulated;
+        }
+        ++n;
+        tis = __dadd_rn(tis, prm.dt);
+        accumulated = __dadd_rn(accumulated, prm.dt);
+      }
+    }
+    prm.n_samples[b] = n;
+  }
+}
+
+__global__ void __launch_bounds__(256) range_eval_kernel(const RangeParams prm) {
+  const int N = prm.N, K = prm.K, D = prm.D, S = prm.max_samples, ND = prm.n_derivs;
+  const long long total = prm.B * S;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    const long long b = idx / S;
+    const int s = int(idx - b * S);
+    const int n = prm.n_samples[b];
+    double* __restrict__ o = prm.out + idx * ND * D;
+    if (s >= n) {  // beyond this trajectory's sample count: defined output (zeros)
+      for (int q = 0; q < ND * D; ++q) o[q] = 0.0;
+      continue;
+    }
+    const int i = prm.seg_idx[idx];
+    const double t = prm.t_local[idx];
+    for (int q = 0; q < ND; ++q) {
+      const int der = prm.derivs[q];
+      for (int d = 0; d < D; ++d) {
+        double acc = 0.0;
+        if (der < N) {
+          const double* __restrict__ c = prm.coeffs + ((b * K + i) * D + d) * N;
+          double bc = 1.0;  // B(der, N-1) = (N-1)!/(N-1-der)!   (exact in fp64)
+          for (int w = 0; w < der; ++w) bc *= double(N - 1 - w);
+          acc = __dmul_rn(bc, c[N - 1]);
+          for (int j = N - 2; j >= der; --j) {
+            double bj = 1.0;
+            for (int w = 0; w < der; ++w) bj *= double(j - w);
+            acc = __dmul_rn(acc, t);
+            acc = __dadd_rn(acc, __dmul_rn(bj, c[j]));
+          }
+        }
+        o[q * D + d] = acc;
+      }
+    }
+  }
+}
+
 // computeCost() (linear_impl.h:123-140): 0.5 * sum c^T Q(T) c with
 // Q[a][b] = 2 B(r,a) B(r,b) T^(a+b-2r+1) / (a+b-2r+1)   (:567-583).
 struct CostParams {

@@ -449,14 +449,38 @@ Eigen::VectorXd Trajectory::evaluate(double t, int derivative_order) const {
 
 void Trajectory::evaluateRange(double t_start, double t_end, double dt, int derivative_order,
                                std::vector<Eigen::VectorXd>* result, std::vector<double>* sampling_times) const {
+  // The reference's walk (src/trajectory.cpp:81-141), kept step for step so that sample counts and sample
+  // times are identical for drop-in callers: the sample clock `accumulated_time` starts at the START of the
+  // segment that contains t_start, advances by dt per sample, is what the loop compares with t_end (so t_end
+  // itself is excluded) and what sampling_times reports; a sample whose local time exceeds the segment time
+  // moves to the next segment; the walk ends after the last segment.  mtg_evaluate_range_batch_f64 is the
+  // batched device version of exactly this loop.
   CHECK_NOTNULL(result)->clear();
   if (sampling_times) sampling_times->clear();
-  CHECK_GT(dt, 0.0);
-  const size_t n = static_cast<size_t>(std::floor((t_end - t_start) / dt + 1e-9)) + 1;
-  for (size_t k = 0; k < n; ++k) {
-    const double t = t_start + static_cast<double>(k) * dt;
-    result->push_back(evaluate(t, derivative_order));
-    if (sampling_times) sampling_times->push_back(t);
+  double accumulated_time = 0.0;
+  size_t i = 0;
+  for (i = 0; i < segments_.size(); ++i) {
+    accumulated_time += segments_[i].getTime();
+    if (accumulated_time > t_start) break;
+  }
+  if (t_start > accumulated_time) {
+    LOG(ERROR) << "Start time out of range of the trajectory!";
+    return;
+  }
+  if (i >= segments_.size()) return;  // t_start == end of the trajectory (the reference reads past the vector here)
+  accumulated_time -= segments_[i].getTime();
+  double time_in_segment = t_start - accumulated_time;
+  while (accumulated_time < t_end) {
+    if (time_in_segment > segments_[i].getTime()) {
+      time_in_segment = time_in_segment - segments_[i].getTime();
+      i++;
+      if (i >= segments_.size()) break;
+      continue;
+    }
+    result->push_back(segments_[i].evaluate(time_in_segment, derivative_order));
+    if (sampling_times) sampling_times->push_back(accumulated_time);
+    time_in_segment += dt;
+    accumulated_time += dt;
   }
 }
 

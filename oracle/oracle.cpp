@@ -703,4 +703,53 @@ int oracle_cpu_info(int32_t* info) {
 
 int oracle_hardware_threads() { return oracle_cpu_info(nullptr); }
 
+// Trajectory::evaluateRange (reference src/trajectory.cpp:81-141) restated literally, quirks included: the
+// sample clock `accumulated_time` starts at the START OF THE SEGMENT that contains t_start (not at t_start),
+// advances by dt per sample and is what the loop compares with t_end and reports as the sampling time;
+// time_in_segment > T moves to the next segment without consuming a sample; the walk stops after the last
+// segment.  Each sample is Segment::evaluate -> Polynomial::evaluate(t, derivative) (polynomial.h:134-149:
+// Horner with separate multiply and add).  times [K], coeffs [K][D][N] -> out [n][D], sampling_times [n]
+// (nullable); returns n (<= max_samples stored), or -1 when t_start lies beyond the trajectory.
+int oracle_evaluate_range(int N, int K, int D, const double* times, const double* coeffs, double t_start, double t_end,
+                          double dt, int derivative, int max_samples, double* out, double* sampling_times) {
+  double accumulated_time = 0.0;
+  int i = 0;
+  for (i = 0; i < K; ++i) {
+    accumulated_time += times[i];
+    if (accumulated_time > t_start) break;
+  }
+  if (t_start > accumulated_time) return -1;
+  if (i >= K) return 0;  // t_start == total time: the reference indexes segments_[size] here (undefined); no samples
+  accumulated_time -= times[i];
+  double time_in_segment = t_start - accumulated_time;
+  int n = 0;
+  while (accumulated_time < t_end) {
+    if (time_in_segment > times[i]) {
+      time_in_segment = time_in_segment - times[i];
+      i++;
+      if (i >= K) break;
+      continue;
+    }
+    if (n < max_samples) {
+      for (int d = 0; d < D; ++d) {
+        const double* c = coeffs + (size_t(i) * D + d) * N;
+        double result = 0.0;
+        if (derivative < N) {
+          result = g_base.v[derivative][N - 1] * c[N - 1];
+          for (int j = N - 2; j >= derivative; --j) {
+            result *= time_in_segment;
+            result += g_base.v[derivative][j] * c[j];
+          }
+        }
+        out[size_t(n) * D + d] = result;
+      }
+      if (sampling_times) sampling_times[n] = accumulated_time;
+    }
+    ++n;
+    time_in_segment += dt;
+    accumulated_time += dt;
+  }
+  return n;
+}
+
 }  // extern "C"

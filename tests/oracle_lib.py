@@ -54,6 +54,9 @@ def lib():
         L.oracle_cost_gradient_mellinger.restype = C.c_int
         L.oracle_cost_gradient_mellinger.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         L.oracle_hardware_threads.restype = C.c_int
+        L.oracle_evaluate_range.restype = C.c_int
+        L.oracle_evaluate_range.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double, C.c_double,
+                                            C.c_int, C.c_int, _dp, _dp]
         L.oracle_cpu_info.restype = C.c_int
         L.oracle_cpu_info.argtypes = [C.c_void_p]
         _lib = L
@@ -254,3 +257,15 @@ def cost_gradient_mellinger(N, r, positions, times):
     if rc != 0:
         raise RuntimeError(f"oracle_cost_gradient_mellinger rc={rc}")
     return float(cost[0]), grad
+
+
+def evaluate_range(times, coeffs, t_start, t_end, dt, derivative, max_samples):
+    """One trajectory: Trajectory::evaluateRange restated (reference src/trajectory.cpp:81-141).
+    times [K], coeffs [K][D][N] -> (n, out [max_samples][D], sampling_times [max_samples])."""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+    K, D, N = coeffs.shape
+    out = np.zeros((max_samples, D))
+    st = np.zeros(max_samples)
+    n = lib().oracle_evaluate_range(N, K, D, times, coeffs, t_start, t_end, dt, derivative, max_samples, out, st)
+    return n, out, st
