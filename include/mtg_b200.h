@@ -59,7 +59,7 @@ extern "C" {
 
 /* which kernel family a problem is routed to (introspection for tests / profiles) */
 #define MTG_KERNEL_WAYPOINT 1     /* specialised block-tridiagonal Cholesky kernels, waypoint topology */
-#define MTG_KERNEL_GENERIC 2      /* arbitrary per-vertex masks, banded Cholesky in global scratch */
+#define MTG_KERNEL_GENERIC 2      /* arbitrary per-vertex masks: masked block-tridiagonal Cholesky */
 #define MTG_KERNEL_NOFREE 3       /* n_free == 0: back-substitution only (linear_impl.h:343-349) */
 
 typedef struct mtg_handle mtg_handle;
@@ -94,14 +94,19 @@ int64_t mtg_launch_count(const mtg_handle* h);
 int mtg_device_is_sm100(const mtg_handle* h);
 
 /* tuning knobs (results are identical to rounding; used by tests and profiles)
- *   MTG_OPT_WAYPOINT_VARIANT: 0 = default (= 3, falling back to 2 when the state does not fit),
+ *   MTG_OPT_WAYPOINT_VARIANT: 0 = default (4 for K <= 8, 3 up to the K whose factor fits on chip, 5 beyond),
  *                             1 = one thread per trajectory, 2 = twisted (state in shared memory),
- *                             3 = twisted with the sweep state in tensor memory + TMA tensor stores. */
+ *                             3 = twisted with the sweep state in tensor memory + TMA tensor stores,
+ *                             4 = persistent version of 3 with deep input prefetch,
+ *                             5 = chunked (checkpoint + recompute) kernel, any K (default for K too large for 3). */
 #define MTG_OPT_WAYPOINT_VARIANT 1
-#define MTG_OPT_RING_DEPTH 2      /* persistent kernel: input ring buffers per thread, 2..4 */
+#define MTG_OPT_RING_DEPTH 2      /* reserved (the persistent kernel is built with a 3-deep input ring) */
 #define MTG_OPT_CTAS_PER_SM 3     /* persistent kernel: cap on resident CTAs per SM, 0 = as many as fit, 9 = one CTA per tile */
 #define MTG_OPT_STAGGER_US 4      /* persistent kernel: spread of the CTA start times, microseconds */
-#define MTG_OPT_DYNAMIC_TILES 5   /* persistent kernel: 1 = warps draw their tiles from a global counter */
+#define MTG_OPT_CHUNK_BLOCKS 6    /* chunked (large-K) kernel: resident vertex blocks per lane, 0 = auto */
+#define MTG_OPT_GENERIC_VARIANT 7 /* arbitrary masks: 0 = masked block kernel (default), 1 = banded kernel in global scratch */
+#define MTG_OPT_MELLINGER_UNFUSED 8 /* 1 = batched Mellinger gradient through expand + solve + cost kernels */
+#define MTG_OPT_DYNAMIC_TILES 5   /* persistent kernel: warps draw tiles from a global counter: 0 = auto, 1 = always, 2 = never */
 int mtg_set_option(mtg_handle* h, int key, int value);
 
 /* ---- host-only layout: the constraint reordering (linear_impl.h:181-260) ---------------- */
@@ -140,7 +145,10 @@ int mtg_compute_cost_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, c
  * PolynomialOptimizationNonLinear::getCostAndGradientMellinger (reference
  * impl/polynomial_optimization_nonlinear_impl.h:286-364): cost[b] = computeCost() at seg_times[b], grad[b][n] =
  * (cost with +0.1 s on segment n and -0.1/(K-1) s on the others, clamped at 0.1 s, re-solved) - cost) / 0.1.
- * The K+1 solves of every trajectory run as one expanded batch through the same kernels.  cost may be NULL. */
+ * The K+1 solves of every trajectory run as ONE cost-only launch over the expanded batch: the perturbed times are
+ * generated inside the kernel and the cost 0.5 d^T H d is accumulated from the solved end-point derivatives, so no
+ * perturbed input and no coefficient is ever written (shapes without a fused kernel take expand + solve + cost
+ * kernels).  cost may be NULL. */
 int mtg_cost_gradient_mellinger_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
                                           const double* d_fixed, double* cost, double* grad, void* stream);
 

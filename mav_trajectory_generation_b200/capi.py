@@ -15,6 +15,9 @@ MTG_OK = 0
 KERNEL_WAYPOINT, KERNEL_GENERIC, KERNEL_NOFREE = 1, 2, 3
 STATUS_BAD_TIME, STATUS_NOT_SPD = 1, 2
 OPT_WAYPOINT_VARIANT = 1
+OPT_RING_DEPTH, OPT_CTAS_PER_SM, OPT_STAGGER_US, OPT_DYNAMIC_TILES, OPT_CHUNK_BLOCKS = 2, 3, 4, 5, 6
+OPT_GENERIC_VARIANT = 7
+OPT_MELLINGER_UNFUSED = 8
 
 EXPORTED_SYMBOLS = [
     "mtg_create", "mtg_destroy", "mtg_last_error", "mtg_launch_count", "mtg_device_is_sm100",

@@ -15,6 +15,8 @@
 #include "mtg_twisted_kernel.cuh"
 #include "mtg_twisted_tmem_kernel.cuh"
 #include "mtg_twisted_tmem_v4_kernel.cuh"
+#include "mtg_twisted_chunked_kernel.cuh"
+#include "mtg_masked_block_kernel.cuh"
 #include "mtg_waypoint_kernel.cuh"
 
 namespace {
@@ -25,6 +27,7 @@ struct Layout {
   int n_all = 0, n_fixed = 0, n_free = 0, bw = 0;
   bool waypoint = false;
   std::vector<int32_t> slot_col;
+  std::vector<int32_t> vcol;  // [(K+1)*h] column of (vertex, derivative)
 };
 
 struct CachedTopology {
@@ -32,6 +35,7 @@ struct CachedTopology {
   int N = 0, K = 0;
   Layout layout;
   int32_t* d_slot_col = nullptr;
+  int32_t* d_vcol = nullptr;
 };
 
 }  // namespace
@@ -47,6 +51,9 @@ struct mtg_handle {
   int ring_depth = 3;        // MTG_OPT_RING_DEPTH (v4 kernel: cp.async input ring buffers, 2..4)
   int ctas_per_sm = 0;       // MTG_OPT_CTAS_PER_SM (v4 kernel: 0 = as many as fit, 9 = one CTA per tile, not persistent)
   int stagger_us = 0;        // MTG_OPT_STAGGER_US (v4 kernel: CTA start times spread over this many microseconds)
+  int mellinger_unfused = 0; // MTG_OPT_MELLINGER_UNFUSED (1 = expand + solve + cost kernels, the round-1 path)
+  int generic_variant = 0;   // MTG_OPT_GENERIC_VARIANT (0 = masked block kernel, 1 = banded kernel in global scratch)
+  int chunk_blocks = 0;      // MTG_OPT_CHUNK_BLOCKS (chunked kernel: resident vertex blocks per lane, 0 = auto)
   int dynamic_tiles = 0;     // MTG_OPT_DYNAMIC_TILES (v4 kernel: warps draw tiles from a global counter)
   unsigned long long* tile_counters = nullptr;  // one per pipeline slot (+ caller stream)
   std::vector<CachedTopology> topologies;
@@ -73,6 +80,9 @@ struct mtg_handle {
     bool attr_plain = false, attr_fused = false;
   };
   std::vector<TmemPlan> plans;
+  // cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION (shared by every K routed to it):
+  // remember the largest value set so far and only ever raise it
+  std::vector<std::pair<const void*, size_t>> smem_set;
   // last encoded tensor map (B = 1 solveLinear() calls re-use the same output buffer)
   struct TmapKey {
     const void* base = nullptr;
@@ -133,6 +143,7 @@ void compute_layout(int N, int K, const std::vector<uint8_t>& mask, Layout* L) {
   for (size_t i = 0; i < mask.size(); ++i) (mask[i] ? nf : np)++;
   int cf = 0, cp = 0;
   for (size_t i = 0; i < mask.size(); ++i) col[i] = mask[i] ? cf++ : nf + cp++;
+  L->vcol = col;
   L->n_all = K * N;
   L->n_fixed = nf;
   L->n_free = np;
@@ -166,19 +177,21 @@ struct WaypointEntry {
   void (*fn_tmem)(const mtg::WaypointParams, const mtg::TmemLaunch, const CUtensorMap);  // + TMEM state, TMA stores
   int stage_bytes_per_warp;
   void (*fn_tmem_fused)(const mtg::WaypointParams, const mtg::TmemLaunch, const CUtensorMap);  // + fused Nfabian
+  void (*fn_chunked)(const mtg::WaypointParams, const mtg::ChunkedLaunch, const CUtensorMap);  // any K (K3)
 };
 #define MTG_WP(N_, R_, D_)                                                                   \
   {                                                                                          \
     N_, R_, D_, mtg::waypoint_state_slots<N_, D_>(), mtg::waypoint_solve_kernel<N_, R_, D_>, \
         mtg::twisted_solve_kernel<N_, R_, D_>, mtg::twisted_tmem_kernel<N_, R_, D_>,         \
-        mtg::tmem_stage_bytes_per_warp<N_, D_>(), mtg::twisted_tmem_kernel<N_, R_, D_, true> \
+        mtg::tmem_stage_bytes_per_warp<N_, D_>(), mtg::twisted_tmem_kernel<N_, R_, D_, true>, \
+        mtg::twisted_chunked_kernel<N_, R_, D_, 3>                                           \
   }
 // v1 (thread per trajectory) is kept for the headline shapes only (cross-check / profiles)
 #define MTG_WP2(N_, R_, D_)                                                                           \
   {                                                                                                   \
     N_, R_, D_, mtg::waypoint_state_slots<N_, D_>(), nullptr, mtg::twisted_solve_kernel<N_, R_, D_>,  \
         mtg::twisted_tmem_kernel<N_, R_, D_>, mtg::tmem_stage_bytes_per_warp<N_, D_>(),               \
-        mtg::twisted_tmem_kernel<N_, R_, D_, true>                                                    \
+        mtg::twisted_tmem_kernel<N_, R_, D_, true>, mtg::twisted_chunked_kernel<N_, R_, D_, 3>        \
   }
 const WaypointEntry kWaypointKernels[] = {
     MTG_WP(10, 4, 3),  MTG_WP(10, 4, 1),  MTG_WP2(10, 4, 2), MTG_WP2(10, 4, 4),   // min snap, N = 10
@@ -188,22 +201,37 @@ const WaypointEntry kWaypointKernels[] = {
     MTG_WP2(6, 2, 3),  MTG_WP2(6, 2, 1),                                          // min acceleration, N = 6
 };
 
-// ---- v4 (persistent) kernels: instantiated for the BASELINE shapes
+// ---- cost-only kernels (computeCost of the solution without writing coefficients; Mellinger expansion on the fly)
+typedef void (*TmemKernel)(const mtg::WaypointParams, const mtg::TmemLaunch, const CUtensorMap);
+struct CostEntry {
+  int N, R, D;
+  TmemKernel fn;
+};
+#define MTG_COST(N_, R_, D_) {N_, R_, D_, mtg::twisted_tmem_kernel<N_, R_, D_, false, true>}
+const CostEntry kCostKernels[] = {MTG_COST(10, 4, 3), MTG_COST(10, 4, 1), MTG_COST(10, 4, 4), MTG_COST(10, 3, 3),
+                                  MTG_COST(10, 2, 3), MTG_COST(8, 3, 3),  MTG_COST(12, 5, 3)};
+const CostEntry* find_cost(const mtg_problem* p) {
+  for (const auto& e : kCostKernels)
+    if (e.N == p->N && e.R == p->r && e.D == p->D) return &e;
+  return nullptr;
+}
+
+// ---- v4 (persistent, deep input prefetch) kernels: the default for short trajectories (K <= 8), where the per-tile
+// prologue of the per-tile kernel is a large share of a tile (profiles/r02_k1_variants.json: C2 +11 %, C4 +18 %;
+// at K = 16 the per-tile kernel is 5 % faster and stays the default)
 typedef void (*V4Kernel)(const mtg::WaypointParams, const mtg::TmemLaunchV4, const CUtensorMap);
 struct V4Entry {
   int N, R, D;
-  V4Kernel fn[3];        // ring depth 2, 3, 4
-  V4Kernel fn_fused[3];
+  V4Kernel fn, fn_fused;
 };
-#define MTG_V4(N_, R_, D_, MB_)                                                                               \
-  {                                                                                                           \
-    N_, R_, D_,                                                                                               \
-        {mtg::twisted_tmem_v4_kernel<N_, R_, D_, false, 2, MB_>, mtg::twisted_tmem_v4_kernel<N_, R_, D_, false, 3, MB_>, \
-         mtg::twisted_tmem_v4_kernel<N_, R_, D_, false, 4, MB_>},                                             \
-        {mtg::twisted_tmem_v4_kernel<N_, R_, D_, true, 2, MB_>, mtg::twisted_tmem_v4_kernel<N_, R_, D_, true, 3, MB_>,   \
-         mtg::twisted_tmem_v4_kernel<N_, R_, D_, true, 4, MB_>}                                               \
+#define MTG_V4(N_, R_, D_, MB_)                                                                    \
+  {                                                                                                \
+    N_, R_, D_, mtg::twisted_tmem_v4_kernel<N_, R_, D_, false, 3, MB_>,                           \
+        mtg::twisted_tmem_v4_kernel<N_, R_, D_, true, 3, MB_>                                      \
   }
-const V4Entry kV4Kernels[] = {MTG_V4(10, 4, 3, 2), MTG_V4(8, 3, 3, 3)};
+const V4Entry kV4Kernels[] = {MTG_V4(10, 4, 3, 2), MTG_V4(8, 3, 3, 3), MTG_V4(10, 4, 1, 2), MTG_V4(10, 3, 3, 2),
+                              MTG_V4(10, 2, 3, 2), MTG_V4(12, 5, 3, 2)};
+constexpr int kV4MaxK = 8;
 
 const V4Entry* find_v4(const mtg_problem* p) {
   for (const auto& e : kV4Kernels)
@@ -214,10 +242,8 @@ const V4Entry* find_v4(const mtg_problem* p) {
 const WaypointEntry* find_waypoint(const mtg_handle* h, const mtg_problem* p, const Layout& L) {
   if (!L.waypoint) return nullptr;
   for (const auto& e : kWaypointKernels)
-    if (e.N == p->N && e.R == p->r && e.D == p->D) {
-      const size_t smem = size_t((p->K + 1) / 2 - 1) * e.slots * 32 * sizeof(double);  // twisted variant
-      if (smem <= h->smem_optin) return &e;
-    }
+    if (e.N == p->N && e.R == p->r && e.D == p->D) return &e;  // any K: the chunked kernel has a fixed footprint
+  (void)h;
   return nullptr;
 }
 
@@ -242,7 +268,12 @@ CachedTopology* get_topology(mtg_handle* h, const mtg_problem* p) {
               cudaMemcpy(t.d_slot_col, t.layout.slot_col.data(), sizeof(int32_t) * t.layout.slot_col.size(),
                          cudaMemcpyHostToDevice)))
     return nullptr;
+  if (set_err(h, "cudaMalloc(vcol)", cudaMalloc(&t.d_vcol, sizeof(int32_t) * t.layout.vcol.size()))) return nullptr;
+  if (set_err(h, "cudaMemcpy(vcol)", cudaMemcpy(t.d_vcol, t.layout.vcol.data(), sizeof(int32_t) * t.layout.vcol.size(),
+                                                cudaMemcpyHostToDevice)))
+    return nullptr;
   if (h->topologies.size() >= 64) {  // bound the cache
+    cudaFree(h->topologies.front().d_vcol);
     cudaFree(h->topologies.front().d_slot_col);
     h->topologies.erase(h->topologies.begin());
   }
@@ -275,6 +306,20 @@ int arena_release(mtg_handle* h, mtg_handle::Arena& a, cudaStream_t stream) {
   return MTG_OK;
 }
 
+// Make sure `fn` may be launched with `bytes` of dynamic shared memory (raises the function attribute when needed).
+int ensure_dyn_smem(mtg_handle* h, const void* fn, size_t bytes) {
+  for (auto& kv : h->smem_set)
+    if (kv.first == fn) {
+      if (kv.second >= bytes) return MTG_OK;
+      MTG_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      kv.second = bytes;
+      return MTG_OK;
+    }
+  MTG_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  h->smem_set.emplace_back(fn, bytes);
+  return MTG_OK;
+}
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
@@ -288,7 +333,8 @@ struct DeviceGuard {
 };
 
 // coeffs as a 2-D fp64 tensor [B][K*D*N] for the TMA stores (box = 16 trajectories x one segment)
-int encode_coeff_tmap(mtg_handle* h, CUtensorMap* out, double* coeffs, int64_t B, const mtg_problem* p) {
+int encode_coeff_tmap(mtg_handle* h, CUtensorMap* out, double* coeffs, int64_t B, const mtg_problem* p,
+                      int box_inner = 0) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -308,7 +354,7 @@ int encode_coeff_tmap(mtg_handle* h, CUtensorMap* out, double* coeffs, int64_t B
   const cuuint64_t row = cuuint64_t(p->K) * p->D * p->N;
   const cuuint64_t dims[2] = {row, cuuint64_t(B)};
   const cuuint64_t strides[1] = {row * sizeof(double)};
-  const cuuint32_t box[2] = {cuuint32_t(p->D * p->N), 16u};
+  const cuuint32_t box[2] = {cuuint32_t(box_inner > 0 ? box_inner : p->D * p->N), 16u};
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult cr = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, coeffs, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -326,6 +372,214 @@ struct FusedInput {
   double* times_out;
 };
 
+// K3: the chunked (checkpoint + recompute) twisted kernel -- any K, fixed on-chip footprint.
+int launch_chunked(mtg_handle* h, const mtg_problem* p, const WaypointEntry* e, const mtg::WaypointParams& prm,
+                   double* coeffs, int64_t B, cudaStream_t stream, int slot) {
+  const int hh = p->N / 2, mm = hh - 1, D = p->D, rd = 3;
+  const int kslots = mm * (mm + 1) / 2 + mm * D + D, kck = mm * mm + mm * D;
+  const int nmax = (p->K + 1) / 2 - 1;
+  cudaFuncAttributes attr;
+  MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)e->fn_chunked));
+  const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
+  auto smem_of = [&](int C, int ntm) {
+    return size_t(mtg::kTmemHeaderBytes) + size_t(4) * e->stage_bytes_per_warp +
+           size_t(rd * (1 + D) + (C + 1) + (D + 1) + (1 + 2 * D) + (C - ntm) * kslots) * mtg::kTmemThreads * 8;
+  };
+  int best_ctas = 0, best_C = 0, best_cols = 0, best_ntm = 0;
+  size_t best_smem = 0;
+  const int cmax = std::max(1, std::min(nmax, 24));
+  const int col_options[] = {256, 512, 128, 64, 0};
+  for (int cols : col_options)
+    for (int C = cmax; C >= 1; --C) {
+      if (h->chunk_blocks > 0 && C != std::min(h->chunk_blocks, cmax)) continue;
+      const int ntm = cols ? std::min(C, cols / (2 * kslots)) : 0;
+      const size_t smem = smem_of(C, ntm);
+      if (smem > h->smem_optin) continue;
+      int ctas = std::min<int>(by_regs, int((228 * 1024) / (smem + 1024)));
+      if (cols) ctas = std::min(ctas, 512 / cols);
+      ctas = std::min(ctas, 8);
+      // More resident CTAs first.  Then: when the sweep needs several rounds anyway, the chunk that fits tensor memory
+      // entirely (no shared-memory blocks: 60 KB per CTA instead of 114 KB leaves ~100 KB of L1 for the re-read
+      // inputs and checkpoints -- measured at K = 50: 0.376 of the HBM roofline with C = 4 vs 0.255 with C = 7);
+      // a single round (C >= nmax) always wins over recomputation.
+      const bool single = C >= nmax, best_single = best_C >= nmax && best_C > 0;
+      const bool all_tmem = ntm == C, best_all_tmem = best_ntm == best_C;
+      bool better = ctas > best_ctas;
+      if (ctas == best_ctas && ctas > 0) {
+        if (single != best_single) better = single;
+        else if (!single && all_tmem != best_all_tmem) better = all_tmem;
+        else better = C > best_C;
+      }
+      if (better) {
+        best_ctas = ctas;
+        best_C = C;
+        best_cols = cols;
+        best_ntm = ntm;
+        best_smem = smem;
+      }
+    }
+  if (best_ctas == 0) {
+    h->error = "chunked kernel: no launch configuration fits";
+    return MTG_ERR_ALLOC;
+  }
+  const int64_t ctiles = (B + 63) / 64;
+  const int64_t blocks = std::min<int64_t>(ctiles, int64_t(best_ctas) * h->sm_count);
+  const int nc = nmax > 0 ? (nmax + best_C - 1) / best_C : 1;
+  mtg::ChunkedLaunch cl;
+  cl.chunk = best_C;
+  cl.n_tmem_blocks = best_ntm;
+  cl.tmem_cols = best_cols;
+  cl.ckpt = nullptr;
+  mtg_handle::Arena& ar = h->scratch[slot];
+  if (nc > 1) {
+    const size_t bytes = size_t(nc - 1) * kck * size_t(blocks) * mtg::kTmemThreads * sizeof(double);
+    const int rc = arena_acquire(h, ar, bytes, stream);
+    if (rc != MTG_OK) return rc;
+    cl.ckpt = ar.p;
+  }
+  {
+        const int rc_smem = ensure_dyn_smem(h, (const void*)e->fn_chunked, size_t(best_smem));
+        if (rc_smem != MTG_OK) return rc_smem;
+      }
+  CUtensorMap tmap;
+  {
+    const int rc = encode_coeff_tmap(h, &tmap, coeffs, B, p);
+    if (rc != MTG_OK) return rc;
+  }
+  e->fn_chunked<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, cl, tmap);
+  MTG_CUDA(h, cudaGetLastError());
+  h->launches++;
+  if (nc > 1) return arena_release(h, ar, stream);
+  return MTG_OK;
+}
+
+// ---- K4: masked block-tridiagonal kernel, any mask; N in {2..12}, dimension groups of 1..4
+typedef void (*MaskedKernel)(const mtg::MaskedParams, const CUtensorMap);
+#define MTG_MASKED_ROW(N_)                                                                                  \
+  {                                                                                                         \
+    mtg::masked_block_kernel<N_, 1>, mtg::masked_block_kernel<N_, 2>, mtg::masked_block_kernel<N_, 3>,     \
+        mtg::masked_block_kernel<N_, 4>                                                                     \
+  }
+const MaskedKernel kMaskedKernels[6][4] = {MTG_MASKED_ROW(2), MTG_MASKED_ROW(4),  MTG_MASKED_ROW(6),
+                                           MTG_MASKED_ROW(8), MTG_MASKED_ROW(10), MTG_MASKED_ROW(12)};
+
+int launch_masked(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int64_t B, const double* times,
+                  const double* dfix, double* coeffs, double* dfree, int32_t* status, cudaStream_t stream, int slot) {
+  const Layout& L = topo->layout;
+  const int hh = p->N / 2;
+  mtg::MaskedParams prm;
+  prm.N = p->N;
+  prm.r = p->r;
+  prm.K = p->K;
+  prm.D = p->D;
+  prm.n_fixed = L.n_fixed;
+  prm.n_free = L.n_free;
+  prm.B = B;
+  prm.vcol = topo->d_vcol;
+  prm.times = times;
+  prm.dfix = dfix;
+  prm.coeffs = coeffs;
+  prm.dfree = dfree;
+  prm.status = status;
+  mtg_handle::Arena& ar = h->scratch[slot];
+  for (int d0 = 0; d0 < p->D;) {
+    const int rem = p->D - d0;
+    const int dg = rem > 4 ? (rem == 5 ? 3 : 4) : rem;  // 5 = 3 + 2 rather than 4 + 1
+    MaskedKernel fn = kMaskedKernels[p->N / 2 - 1][dg - 1];
+    const size_t smem = size_t(4) * 32 * dg * p->N * sizeof(double);
+    {
+        const int rc_smem = ensure_dyn_smem(h, (const void*)fn, size_t(smem));
+        if (rc_smem != MTG_OK) return rc_smem;
+      }
+    int per_sm = 0;
+    MTG_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, 128, smem));
+    per_sm = std::max(per_sm, 1);
+    const int64_t blocks = std::min<int64_t>((B + 127) / 128, int64_t(per_sm) * h->sm_count);
+    const int kslots = hh * (hh + 1) / 2 + hh * dg;
+    const size_t bytes = size_t(p->K + 1) * kslots * size_t(blocks) * 128 * sizeof(double);
+    int rc = arena_acquire(h, ar, bytes, stream);
+    if (rc != MTG_OK) return rc;
+    prm.lifo = ar.p;
+    prm.d0 = d0;
+    CUtensorMap tmap;
+    rc = encode_coeff_tmap(h, &tmap, coeffs, B, p, dg * p->N);
+    if (rc != MTG_OK) return rc;
+    fn<<<(unsigned)blocks, 128, smem, stream>>>(prm, tmap);
+    MTG_CUDA(h, cudaGetLastError());
+    h->launches++;
+    rc = arena_release(h, ar, stream);
+    if (rc != MTG_OK) return rc;
+    d0 += dg;
+  }
+  return MTG_OK;
+}
+
+// Fused cost-only solve: nx problems -> cost_x[nx].  With mel_k1 > 0 the nx = B * mel_k1 problems
+// are the Mellinger expansion of the B trajectories in (times, dfix), generated inside the kernel.
+// Returns MTG_ERR_ALLOC when no fused kernel / launch configuration exists (caller falls back).
+int launch_cost_fused(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int64_t nx, const double* times,
+                      const double* dfix, double* cost_x, int mel_k1, double inc, double lower, cudaStream_t stream) {
+  const Layout& L = topo->layout;
+  const CostEntry* ce = find_cost(p);
+  const WaypointEntry* e = L.waypoint ? find_waypoint(h, p, L) : nullptr;
+  if (!ce || !e || L.n_free == 0) return MTG_ERR_ALLOC;
+  const int nmax = (p->K + 1) / 2 - 1;
+  cudaFuncAttributes attr;
+  MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)ce->fn));
+  const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
+  int best_ctas = 0, best_cols = 0, best_ntm = 0;
+  size_t best_smem = 0;
+  const int col_options[] = {512, 256, 128, 64, 32, 0};
+  for (int cols : col_options) {
+    const int tslots = e->slots + e->D;
+    const int ntm = cols ? std::min(nmax, cols / (2 * tslots)) : 0;
+    if (cols && ntm == 0) continue;
+    const size_t smem = mtg::kTmemHeaderBytes + size_t(4) * e->stage_bytes_per_warp +
+                        size_t(2) * (1 + p->D) * mtg::kTmemThreads * 8 + size_t(nmax + 1) * mtg::kTmemThreads * 8 +
+                        size_t(nmax - ntm) * tslots * mtg::kTmemThreads * sizeof(double);
+    if (smem > h->smem_optin) continue;
+    int ctas = std::min<int>(by_regs, int((228 * 1024) / (smem + 1024)));
+    ctas = std::min(ctas, 16);
+    if (cols) ctas = std::min(ctas, 512 / cols);
+    if (ctas > best_ctas || (ctas == best_ctas && smem < best_smem)) {
+      best_ctas = ctas;
+      best_cols = cols;
+      best_ntm = ntm;
+      best_smem = smem;
+    }
+  }
+  if (best_ctas < 2) return MTG_ERR_ALLOC;  // large K: unfused path (chunked kernel + cost kernel)
+  mtg::WaypointParams prm;
+  prm.K = p->K;
+  prm.n_fixed = L.n_fixed;
+  prm.B = nx;
+  prm.times = times;
+  prm.dfix = dfix;
+  prm.coeffs = nullptr;
+  prm.dfree = nullptr;
+  prm.status = nullptr;
+  prm.positions = nullptr;
+  prm.v_max = prm.a_max = prm.magic = 0.0;
+  prm.times_out = nullptr;
+  prm.cost = cost_x;
+  prm.mel_k1 = mel_k1;
+  prm.mel_inc = inc;
+  prm.mel_lower = lower;
+  mtg::TmemLaunch tl;
+  tl.n_tmem_blocks = best_ntm;
+  tl.tmem_cols = best_cols;
+  {
+        const int rc_smem = ensure_dyn_smem(h, (const void*)ce->fn, size_t(best_smem));
+        if (rc_smem != MTG_OK) return rc_smem;
+      }
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));  // unused by the cost-only instantiation
+  ce->fn<<<(unsigned)((nx + 63) / 64), mtg::kTmemThreads, best_smem, stream>>>(prm, tl, tmap);
+  MTG_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return MTG_OK;
+}
+
 int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int64_t B, const double* times,
                  const double* dfix, const double* dfree_in, double* coeffs, double* dfree, int32_t* status,
                  cudaStream_t stream, bool backsub_only, const FusedInput* fused = nullptr,
@@ -335,7 +589,15 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
   // clear a stale (non-sticky) error another library of the process may have left behind: the
   // cudaGetLastError() after our launches must report OUR launch only
   (void)cudaGetLastError();
-  const int kind = backsub_only ? MTG_KERNEL_NOFREE : route(h, p, L);
+  int kind = backsub_only ? MTG_KERNEL_NOFREE : route(h, p, L);
+  // The TMA tensor stores of the TMEM / chunked kernels need a 16-byte aligned output; an 8-byte aligned caller
+  // buffer (e.g. a tensor slice) takes the shared-memory twisted kernel when its state fits, else the generic one.
+  const bool out_aligned = (reinterpret_cast<uintptr_t>(coeffs) & 15u) == 0;
+  if (kind == MTG_KERNEL_WAYPOINT && !fused) {
+    const WaypointEntry* e0 = find_waypoint(h, p, L);
+    const bool twisted_fits = size_t((p->K + 1) / 2 - 1) * e0->slots * 32 * sizeof(double) <= h->smem_optin;
+    if (!out_aligned && !twisted_fits) kind = MTG_KERNEL_GENERIC;
+  }
   if (kind == MTG_KERNEL_WAYPOINT) {
     const WaypointEntry* e = find_waypoint(h, p, L);
     mtg::WaypointParams prm;
@@ -352,16 +614,21 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
     prm.a_max = fused ? fused->a_max : 0.0;
     prm.magic = fused ? fused->magic : 0.0;
     prm.times_out = fused ? fused->times_out : nullptr;
+    prm.cost = nullptr;
+    prm.mel_k1 = 0;
+    prm.mel_inc = prm.mel_lower = 0.0;
     const size_t smem_v1 = size_t(p->K - 1) * e->slots * 32 * sizeof(double);
     const bool use_v1 = h->waypoint_variant == 1 && e->fn != nullptr && smem_v1 <= h->smem_optin;
     // The TMA tensor stores need a 16-byte aligned output (cuTensorMapEncodeTiled); an 8-byte aligned
     // caller buffer (e.g. a tensor slice) takes the shared-memory twisted kernel instead of failing.
     const bool coeffs_aligned = (reinterpret_cast<uintptr_t>(coeffs) & 15u) == 0;
-    if (h->waypoint_variant == 4 && coeffs_aligned) {
+    if (h->waypoint_variant == 5 && coeffs_aligned && !fused)
+      return launch_chunked(h, p, e, prm, coeffs, B, stream, slot);
+    if ((h->waypoint_variant == 4 || (h->waypoint_variant == 0 && p->K <= kV4MaxK)) && coeffs_aligned) {
       const V4Entry* e4 = find_v4(p);
       if (e4) {
-        const int rd = h->ring_depth;
-        V4Kernel fn = (fused ? e4->fn_fused : e4->fn)[rd - 2];
+        V4Kernel fn = fused ? e4->fn_fused : e4->fn;
+        const int rd = 3;
         const int hh = p->N / 2, mm = hh - 1;
         const int kslots = mm * (mm + 1) / 2 + mm * p->D + p->D, kpro = 2 * p->D + mm * p->D + 1;
         const int nmax = (p->K + 1) / 2 - 1;
@@ -396,13 +663,19 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
           tl.tmem_cols = best_cols;
           tl.region_slots = 0;
           tl.tile_counter = nullptr;
-          tl.stagger_ns = per_tile ? 0u : unsigned(h->stagger_us) * 1000u;
-          if (h->dynamic_tiles && !per_tile) {
+          // dynamic tile counter when every warp has many tiles to draw (balances the tail); static round-robin for
+          // small batches, where the first draw's round trip to L2 is not amortised (measured: C2 static, C4 dynamic)
+          const int64_t tiles_per_warp = ((B + 15) / 16) / std::max<int64_t>(1, int64_t(best_ctas) * h->sm_count * 4);
+          const bool dyn = h->dynamic_tiles == 1 || (h->dynamic_tiles == 0 && tiles_per_warp >= 16);
+          if (dyn && !per_tile) {
             if (!h->tile_counters) MTG_CUDA(h, cudaMalloc(&h->tile_counters, sizeof(unsigned long long) * 32 * (mtg_handle::kPipe + 1)));
             tl.tile_counter = h->tile_counters + 32 * slot;  // 256-byte apart
             MTG_CUDA(h, cudaMemsetAsync(tl.tile_counter, 0, sizeof(unsigned long long), stream));
           }
-          MTG_CUDA(h, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem));
+          {
+        const int rc_smem = ensure_dyn_smem(h, (const void*)fn, size_t(best_smem));
+        if (rc_smem != MTG_OK) return rc_smem;
+      }
           CUtensorMap tmap;
           {
             const int rc = encode_coeff_tmap(h, &tmap, coeffs, B, p);
@@ -417,7 +690,10 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
         }
       }
     }
-    if ((h->waypoint_variant == 0 || h->waypoint_variant == 3 || fused) && (coeffs_aligned || fused)) {
+    const bool twisted_fits = size_t((p->K + 1) / 2 - 1) * e->slots * 32 * sizeof(double) <= h->smem_optin;
+    const bool want_default = h->waypoint_variant == 0 || h->waypoint_variant >= 3 || fused ||
+                              (h->waypoint_variant == 2 && !twisted_fits) || (h->waypoint_variant == 1 && !use_v1 && !twisted_fits);
+    if (want_default && (coeffs_aligned || fused)) {
       if (!coeffs_aligned) return MTG_ERR_ALLOC;  // fused entry: caller falls back to pack + solve
       const int nmax = (p->K + 1) / 2 - 1;
       // ---- launch plan (TMEM column count / spill split maximising resident CTAs per SM): computed and
@@ -454,25 +730,17 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
         h->plans.push_back(np);
         plan = &h->plans.back();
       }
-      if (plan->ctas == 0 && fused) return MTG_ERR_ALLOC;  // caller falls back to pack + solve
-      if (plan->ctas == 0) {  // sweep state too large for TMEM + shared memory of a 128-thread CTA
-        const size_t smem = size_t(nmax) * e->slots * 32 * sizeof(double);
-        MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn_twisted, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
-        e->fn_twisted<<<(unsigned)((B + 15) / 16), 32, smem, stream>>>(prm);
-        MTG_CUDA(h, cudaGetLastError());
-        h->launches++;
-        return MTG_OK;
-      }
+      if (plan->ctas < 2 && fused) return MTG_ERR_ALLOC;  // caller falls back to pack + solve
+      if (plan->ctas < 2)  // the whole factor does not fit on chip at two CTAs per SM: checkpoint + recompute (K3)
+        return launch_chunked(h, p, e, prm, coeffs, B, stream, slot);
       mtg::TmemLaunch tl;
       tl.n_tmem_blocks = plan->ntm;
       tl.tmem_cols = plan->cols;
       const int64_t blocks = (B + 63) / 64;
       auto fn = fused ? e->fn_tmem_fused : e->fn_tmem;
-      bool& attr_done = fused ? plan->attr_fused : plan->attr_plain;
-      if (!attr_done) {
-        MTG_CUDA(h, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
-        attr_done = true;
+      {
+        const int rc_smem = ensure_dyn_smem(h, (const void*)fn, plan->smem);
+        if (rc_smem != MTG_OK) return rc_smem;
       }
       // coeffs as a 2-D fp64 tensor [B][K*D*N] for the TMA stores (box = 16 trajectories x one segment);
       // the encoded map is cached for repeated calls on the same output buffer
@@ -491,13 +759,18 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
       }
       fn<<<(unsigned)blocks, mtg::kTmemThreads, plan->smem, stream>>>(prm, tl, h->tmap_cached);
     } else if (use_v1) {
-      MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v1));
+      {
+        const int rc_smem = ensure_dyn_smem(h, (const void*)e->fn, size_t(smem_v1));
+        if (rc_smem != MTG_OK) return rc_smem;
+      }
       const int64_t blocks = (B + 31) / 32;
       e->fn<<<(unsigned)blocks, 32, smem_v1, stream>>>(prm);
     } else {
       const size_t smem = size_t((p->K + 1) / 2 - 1) * e->slots * 32 * sizeof(double);
-      MTG_CUDA(h, cudaFuncSetAttribute((const void*)e->fn_twisted, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+      {
+        const int rc_smem = ensure_dyn_smem(h, (const void*)e->fn_twisted, size_t(smem));
+        if (rc_smem != MTG_OK) return rc_smem;
+      }
       const int64_t blocks = (B + 15) / 16;
       e->fn_twisted<<<(unsigned)blocks, 32, smem, stream>>>(prm);
     }
@@ -505,6 +778,8 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
     h->launches++;
     return MTG_OK;
   }
+  if (kind == MTG_KERNEL_GENERIC && out_aligned && h->generic_variant == 0)
+    return launch_masked(h, p, topo, B, times, dfix, coeffs, dfree, status, stream, slot);
   mtg::GenericParams prm;
   prm.N = p->N;
   prm.r = p->r;
@@ -615,7 +890,10 @@ void mtg_destroy(mtg_handle* h) {
   if (!h) return;
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
-  for (auto& t : h->topologies) cudaFree(t.d_slot_col);
+  for (auto& t : h->topologies) {
+    cudaFree(t.d_slot_col);
+    cudaFree(t.d_vcol);
+  }
   if (h->tile_counters) cudaFree(h->tile_counters);
   for (int i = 0; i <= mtg_handle::kPipe; ++i) {
     for (mtg_handle::Arena* a : {&h->scratch[i], &h->pack[i]}) {
@@ -638,7 +916,19 @@ int mtg_device_is_sm100(const mtg_handle* h) { return h && h->cc_major == 10; }
 
 int mtg_set_option(mtg_handle* h, int key, int value) {
   if (!h) return MTG_ERR_BAD_ARG;
-  if (key == MTG_OPT_WAYPOINT_VARIANT && value >= 0 && value <= 4) {
+  if (key == MTG_OPT_MELLINGER_UNFUSED && (value == 0 || value == 1)) {
+    h->mellinger_unfused = value;
+    return MTG_OK;
+  }
+  if (key == MTG_OPT_GENERIC_VARIANT && (value == 0 || value == 1)) {
+    h->generic_variant = value;
+    return MTG_OK;
+  }
+  if (key == MTG_OPT_CHUNK_BLOCKS && value >= 0 && value <= 64) {
+    h->chunk_blocks = value;
+    return MTG_OK;
+  }
+  if (key == MTG_OPT_WAYPOINT_VARIANT && value >= 0 && value <= 5) {
     h->waypoint_variant = value;
     return MTG_OK;
   }
@@ -654,7 +944,7 @@ int mtg_set_option(mtg_handle* h, int key, int value) {
     h->stagger_us = value;
     return MTG_OK;
   }
-  if (key == MTG_OPT_DYNAMIC_TILES && (value == 0 || value == 1)) {
+  if (key == MTG_OPT_DYNAMIC_TILES && value >= 0 && value <= 2) {  // 0 = auto, 1 = always, 2 = never
     h->dynamic_tiles = value;
     return MTG_OK;
   }
@@ -893,6 +1183,23 @@ int mtg_cost_gradient_mellinger_batch_f64(mtg_handle* h, const mtg_problem* p, i
   const Layout& L = topo->layout;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t K = p->K, D = p->D, N = p->N, nf = L.n_fixed;
+  if (p->K > 1 && h->mellinger_unfused == 0) {
+    // fused path: one cost-only launch over the B*(K+1) expanded problems (expansion generated in the kernel, no
+    // perturbed inputs or coefficients ever written), then the finite differences
+    mtg_handle::Arena& arf = h->pack[mtg_handle::kPipe];
+    int rc = arena_acquire(h, arf, size_t(B) * (K + 1) * 8, s);
+    if (rc != MTG_OK) return rc;
+    rc = launch_cost_fused(h, p, topo, B * int64_t(K + 1), seg_times, d_fixed, arf.p, int(K + 1), 0.1, 0.1, s);
+    if (rc == MTG_OK) {
+      const int threads = 128;
+      const int64_t gb = std::min<int64_t>((B + threads - 1) / threads, int64_t(h->sm_count) * 16);
+      mtg::mellinger_gradient_kernel<<<(unsigned)gb, threads, 0, s>>>(B, p->K, arf.p, cost, grad, 0.1);
+      MTG_CUDA(h, cudaGetLastError());
+      h->launches++;
+      return arena_release(h, arf, s);
+    }
+    if (rc != MTG_ERR_ALLOC) return rc;
+  }
   const size_t per_x = (K + D * nf + K * D * N + 1) * 8;  // times + d_fixed + coeffs + cost of one expanded problem
   int64_t chunk = std::max<int64_t>(1, int64_t((size_t(384) << 20) / (per_x * (K + 1))));
   chunk = std::min<int64_t>(chunk, B);

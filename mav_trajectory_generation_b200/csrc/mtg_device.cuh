@@ -96,6 +96,7 @@ struct H1Imm;
       constexpr double t[] = MTG_H1S_##N_##_##R_;                                                      \
       return t[r * N_ + c];                                                                            \
     }                                                                                                  \
+    static constexpr double scale = MTG_H1S_SCALE_##N_##_##R_; /* table = H(1;r) * scale */            \
   };
 
 MTG_DEF_A1INV(2)

@@ -177,7 +177,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int N, int R, int D, bool FUSED = false>
+template <int N, int R, int D, bool FUSED = false, bool COST = false>
 __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
     twisted_tmem_kernel(const WaypointParams prm, const TmemLaunch tl, const __grid_constant__ CUtensorMap tmap) {
   constexpr int h = N / 2;
@@ -254,9 +254,24 @@ __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
   const bool valid = traj < prm.B;
   if (!valid) traj = prm.B - 1;
 
-  const double* __restrict__ tt = FUSED ? nullptr : prm.times + traj * K;
+  // cost-only mode with the Mellinger expansion generated on the fly: inputs come from the base trajectory
+  long long src = traj;
+  int mel_n = -1;
+  double mel_corr = 0.0;
+  if constexpr (COST) {
+    if (prm.mel_k1 > 0) {
+      src = traj / prm.mel_k1;
+      mel_n = int(traj - src * prm.mel_k1) - 1;
+      mel_corr = prm.mel_inc / (K - 1.0);
+    }
+  }
+  auto time_of = [&](double raw, int seg_index) -> double {  // seg_index: ORIGINAL segment index
+    if constexpr (COST) return mellinger_time(raw, seg_index, mel_n, prm.mel_inc, mel_corr, prm.mel_lower);
+    return raw;
+  };
+  const double* __restrict__ tt = FUSED ? nullptr : prm.times + src * K;
   const double* __restrict__ fx =
-      FUSED ? prm.positions + traj * (long long)(K + 1) * D : prm.dfix + traj * (long long)D * nf;
+      FUSED ? prm.positions + src * (long long)(K + 1) * D : prm.dfix + src * (long long)D * nf;
   auto seg = [&](int j) -> int { return half ? K - 1 - j : j; };
   auto pidx = [&](int v) -> int {
     const int o = half ? K - v : v;
@@ -312,7 +327,40 @@ __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
 
   // emit own-frame segment j for every lane of the warp at once (convergent).  `act`: this lane's
   // values are meaningful; rows of inactive lanes are not stored.  v_step: the sweep step (0 = final).
+  double cost_acc = 0.0;
   auto emit_all = [&](int j, int v_step, double T, double iT, const double (&sd)[h][D], const double (&ed)[h][D]) {
+    if constexpr (COST) {
+      // 0.5 d^T H(T) d of this segment, d = [start derivatives; end derivatives] in the own frame (the cost is
+      // invariant under the time reversal of the odd half): H = T^(1-2r) S G S / scale, S = diag(T^(s mod h)).
+      (void)j;
+      const int nh_own = half ? nhB : nhF;
+      if (v_step <= nh_own) {
+        double tp[h];
+        tp[0] = 1.0;
+#pragma unroll
+        for (int k = 1; k < h; ++k) tp[k] = tp[k - 1] * T;
+        double q = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          double u[N];
+#pragma unroll
+          for (int k = 0; k < h; ++k) {
+            u[k] = tp[k] * sd[k][d];
+            u[h + k] = tp[k] * ed[k][d];
+          }
+#pragma unroll
+          for (int s2 = 0; s2 < N; ++s2) {
+            double row = 0.5 * G::at(s2, s2) * u[s2];
+#pragma unroll
+            for (int t2 = s2 + 1; t2 < N; ++t2) row = fma(G::at(s2, t2), u[t2], row);
+            q = fma(row, u[s2], q);
+          }
+        }
+        // T^(1-2r) = T * (1/T)^(2r)
+        cost_acc = fma(q, T * pow_int<2 * R>(iT), cost_acc);
+      }
+      return;
+    }
     // original orientation: start = J*(own end) for the reversed half; J folded into the powers
     double tp[h], itp[h];
     const double Ts = half ? -T : T;
@@ -382,7 +430,7 @@ __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
     if constexpr (FUSED) {
       T0 = nfabian_time<D>(xm, xc, prm.v_max, prm.a_max, prm.magic);
     } else {
-      T0 = T0e;
+      T0 = time_of(T0e, seg(0));
     }
     if (!(T0 > 0.0)) stat |= kStatusBadTime;
     HT(0) = T0;
@@ -427,7 +475,7 @@ __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
       if constexpr (FUSED) {
         T = nfabian_time<D>(xc, xn, prm.v_max, prm.a_max, prm.magic);
       } else {
-        T = *PF(v & 1, 0);
+        T = time_of(*PF(v & 1, 0), seg(v));
       }
       HT(v) = T;
       {  // prefetch the next step's inputs (clamped indices: never out of bounds)
@@ -740,6 +788,11 @@ __global__ void __launch_bounds__(kTmemThreads, (N <= 8 ? 3 : 2))
     emit_all(0, 0, T, iT, sd, ed);
   }
 
+  if constexpr (COST) {
+    // q accumulated sum_{s<=t} (1 or 1/2) G u u = 0.5 u^T G u per segment: cost = sum over both halves / scale
+    const double other = __shfl_xor_sync(kFull, cost_acc, 1);
+    if (valid && half == 0 && prm.cost != nullptr) prm.cost[traj] = (cost_acc + other) * (1.0 / G::scale);
+  }
   if (lane == 0) bulk_wait_all();  // every TMA store issued by this warp has completed
   if (tl.tmem_cols > 0) {
     tmem::fence_before_sync();

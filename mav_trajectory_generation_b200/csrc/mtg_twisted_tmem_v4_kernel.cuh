@@ -31,7 +31,6 @@ struct TmemLaunchV4 {
   int region_slots;   // doubles per thread of the spill / next-tile-prologue region
   unsigned long long* tile_counter;  // non-null: warps draw their 16-trajectory tiles from this counter (zeroed by
                                      // the host before the launch); null: static round-robin assignment
-  unsigned stagger_ns;               // CTA c starts (c mod 16) / 16 of this many nanoseconds late (see below)
 };
 
 template <int N, int D>
@@ -59,7 +58,7 @@ __device__ __forceinline__ void cp_async_wait_group() {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 
-template <int N, int R, int D, bool FUSED, int RD, int MINB>
+template <int N, int R, int D, bool FUSED, int RD, int MINB, int HOIST = 0>
 __global__ void __launch_bounds__(kTmemThreads, MINB)
     twisted_tmem_v4_kernel(const WaypointParams prm, const TmemLaunchV4 tl, const __grid_constant__ CUtensorMap tmap) {
   constexpr int h = N / 2;
@@ -72,6 +71,12 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
   constexpr int kWarps = kTmemThreads / 32;
   constexpr double kTiny = 0x1p-600, kHuge = 0x1p+600;
   static_assert(RD >= 2, "ring depth");
+  // work overlapped with the asynchronous tensor-memory read of the outward sweep: 0 = none, 1 = segment time and
+  // its powers, 2 = also E_v u_{v+1} (the fetched words stay live meanwhile: ~50 registers).  Measured on C3
+  // (profiles/r02_k1_variants.json): 0.563 / 0.511 / 0.511 of the HBM roofline for 0 / 1 / 2 -- the extra live
+  // registers cost more than the exposed tcgen05.wait::ld, so 0 is the default.
+  constexpr int kHoist = HOIST;
+  constexpr bool kHoistE = HOIST >= 2;
   using G = H1Imm<N, R>;
   using AI = A1InvImm<N>;
 
@@ -120,10 +125,13 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
       for (int i = 0; i < kSlots; ++i) SP(blk - ntm, i) = sv[i];
     }
   };
-  auto get_state = [&](int blk, double (&sv)[kSlots]) {
+  // The tensor-memory read is asynchronous until tcgen05.wait::ld: state_issue() starts it, the caller does the
+  // work that does not depend on the state (segment time, its powers, E_v u_{v+1}), state_finish() waits.
+  auto state_issue = [&](int blk, uint32_t (&w)[kWords]) {
+    if (blk < ntm) tmem::ld_words<kWords>(tbase + uint32_t(blk * kWords), w);
+  };
+  auto state_finish = [&](int blk, const uint32_t (&w)[kWords], double (&sv)[kSlots]) {
     if (blk < ntm) {
-      uint32_t w[kWords];
-      tmem::ld_words<kWords>(tbase + uint32_t(blk * kWords), w);
       tmem::wait_ld();
 #pragma unroll
       for (int i = 0; i < kSlots; ++i) sv[i] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
@@ -141,29 +149,13 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
   auto sgn = [&](int idx) -> double { return (half && !(idx & 1)) ? -1.0 : 1.0; };
   const int e0 = half ? h + K : 1;  // first fixed end-derivative slot of own-frame vertex 0
 
-  // Phase stagger.  A tile alternates a read-only inward sweep with a write-heavy outward sweep; persistent CTAs
-  // that all start together stay in lockstep for the whole launch and turn the output stream (83 % of the HBM
-  // traffic) into bursts.  Spreading the start times over one tile period keeps the write rate flat; with the
-  // dynamic tile counter the late starters simply take fewer tiles.
-  if (tl.stagger_ns) {
-    const unsigned long long delay = (unsigned long long)(blockIdx.x & 15u) * (tl.stagger_ns >> 4);
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    do {
-      __nanosleep(256);
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    } while (t1 - t0 < delay);
-  }
-
   const long long n_wtiles = (prm.B + 15) >> 4;
   const long long wt_stride = (long long)gridDim.x * kWarps;
   const bool dyn = tl.tile_counter != nullptr;
-  auto fetch_tile = [&]() -> long long {
-    long long t = 0;
-    if (lane == 0) t = (long long)atomicAdd(tl.tile_counter, 1ULL);
-    return __shfl_sync(kFull, t, 0);
-  };
-  long long wt = dyn ? fetch_tile() : (long long)blockIdx.x * kWarps + warp;
+  // lane 0 draws the tile; the broadcast is deferred to the first use so that the atomic's round trip to L2
+  // overlaps the sweep
+  auto draw_tile = [&]() -> long long { return lane == 0 ? (long long)atomicAdd(tl.tile_counter, 1ULL) : 0; };
+  long long wt = dyn ? __shfl_sync(kFull, draw_tile(), 0) : (long long)blockIdx.x * kWarps + warp;
 
   // pointers of a warp tile's trajectory for this lane
   struct Ptrs {
@@ -224,7 +216,8 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
   const int v_pro = ntm < nmax ? ntm : nmax;
 
   while (wt < n_wtiles) {
-    const long long wt_next = dyn ? fetch_tile() : wt + wt_stride;  // known one tile ahead: its prologue is prefetched
+    long long wt_next = dyn ? draw_tile() : wt + wt_stride;  // known one tile ahead: its prologue is prefetched
+    bool next_known = !dyn;
     const Ptrs P = tile_ptrs(wt);
     const long long traj0 = wt * 16;
     const bool valid = P.valid;
@@ -564,6 +557,10 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
       cp_async_commit();
     }
     auto maybe_pro = [&](int v) {
+      if (v == v_pro && !next_known) {
+        wt_next = __shfl_sync(kFull, wt_next, 0);
+        next_known = true;
+      }
       if (v == v_pro && wt_next < n_wtiles) {  // warp-uniform
         const Ptrs pn = tile_ptrs(wt_next);
         pro_issue(pn);
@@ -573,21 +570,40 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
     if (nmax == 0) maybe_pro(0);  // v_pro == 0
 
     for (int v = nmax; v >= 1; --v) {
-      double sv[kSlots];
-      get_state(v - 1, sv);
-      maybe_pro(v);
+      uint32_t w[kWords];
+      if constexpr (kHoist > 0) state_issue(v - 1, w);
       const bool act = v <= nh;
-      double T = 1.0, iT = 1.0;
+      // independent of the state being fetched: segment time, its powers, t = E_v u_{v+1}
+      const double T = act ? HT(v) : 1.0;
+      const double iT = fast_rcp(T);
+      double pw[N - 1];
+      segment_powers<N, R>(T, iT, pw);
+      double tE[m][D];
+      auto compute_tE = [&]() {
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+          for (int a = 0; a < m; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < m; ++b) s = fma(pw[a + b + 2] * G::at(1 + a, h + 1 + b), ed[1 + b][d], s);
+            tE[a][d] = s;
+          }
+      };
+      if constexpr (kHoistE) compute_tE();
+      maybe_pro(v);
+      double sv[kSlots];
+      if constexpr (kHoist == 0) state_issue(v - 1, w);
+      state_finish(v - 1, w, sv);
+      if constexpr (!kHoistE) compute_tE();
       double sd[h][D];
       if (act) {
         double xv[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) xv[d] = sv[kL + m * D + d];
-        T = HT(v);
         if constexpr (FUSED) {
           if (tout != nullptr && valid) tout[seg(v)] = T;
         }
-        iT = fast_rcp(T);
         double L[m][m], inv[m], rhs[m][D];
         {
           int slot = 0;
@@ -602,21 +618,12 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
 #pragma unroll
             for (int d = 0; d < D; ++d) rhs[j][d] = sv[slot++];
         }
-        double pw[N - 1];
-        segment_powers<N, R>(T, iT, pw);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           double t[m];
 #pragma unroll
-          for (int a = 0; a < m; ++a) {
-            double s = 0.0;
-#pragma unroll
-            for (int b = 0; b < m; ++b) s = fma(pw[a + b + 2] * G::at(1 + a, h + 1 + b), ed[1 + b][d], s);
-            t[a] = s;
-          }
-#pragma unroll
           for (int j = 0; j < m; ++j) {
-            double s = t[j];
+            double s = tE[j][d];
 #pragma unroll
             for (int k = 0; k < j; ++k) s = fma(-L[j][k], t[k], s);
             t[j] = s * inv[j];

@@ -48,7 +48,21 @@ struct WaypointParams {
   const double* __restrict__ positions;
   double v_max, a_max, magic;
   double* __restrict__ times_out;     // [B][K] or null
+  // cost-only mode (the nonlinear optimiser's inner loop): no coefficients are written; the
+  // kernel returns computeCost() of every problem.  With mel_k1 = K+1 the batch is the Mellinger expansion
+  // (reference impl/polynomial_optimization_nonlinear_impl.h:286-364) generated on the fly: problem q belongs to
+  // trajectory q / (K+1); variant n = q % (K+1) - 1 (n = -1: unperturbed) adds mel_inc to segment n, subtracts
+  // mel_inc / (K-1) from the others and clamps at mel_lower -- `times` / `dfix` are the UNEXPANDED arrays.
+  double* __restrict__ cost;          // [B] or null
+  int mel_k1;
+  double mel_inc, mel_lower;
 };
+
+__device__ __forceinline__ double mellinger_time(double t, int i, int n, double inc, double corr, double lower) {
+  if (n < 0) return t;
+  const double v = (i == n) ? t + inc : t - corr;
+  return v > lower ? v : lower;  // std::max(kOptimizationTimeLowerBound, t)
+}
 
 // t = distance / v_max * 2 * (1 + magic * v_max / a_max * exp(-distance / v_max * 2)), evaluated in the
 // reference's order with no FMA contraction (the CPU oracle is built with -ffp-contract=off).

@@ -58,7 +58,8 @@ def test_layout_matches_oracle_for_random_masks(oracle):
 def test_routing():
     assert m.Problem(10, 4, 1, 3).kernel == m.KERNEL_NOFREE          # single fully constrained segment
     assert m.Problem(10, 4, 50, 3).kernel == m.KERNEL_WAYPOINT       # twisted sweep state still fits
-    assert m.Problem(10, 4, 100, 3).kernel == m.KERNEL_GENERIC       # state does not fit shared memory
+    assert m.Problem(10, 4, 100, 3).kernel == m.KERNEL_WAYPOINT      # any K: chunked (checkpoint + recompute) kernel
+    assert m.Problem(10, 4, 1000, 3).kernel == m.KERNEL_WAYPOINT
     assert m.Problem(10, 1, 16, 3).kernel == m.KERNEL_GENERIC        # (N, r) without a specialised kernel
     mask = np.zeros((5, 5), dtype=np.uint8)
     mask[:, 0] = 1

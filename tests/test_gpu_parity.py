@@ -12,6 +12,14 @@ TOL = 1e-10          # north_star: coefficients within 1e-10 (global-relative) o
 BASELINE_SHAPES = {(10, 4, 16, 3), (10, 4, 8, 3), (8, 3, 4, 3), (10, 4, 2, 3)}   # C3, C2, C4, C1
 
 
+def global_rel_err(a, b):
+    """per-trajectory max|a-b| / max|b|   (a, b: [B][K][D][N])"""
+    B = a.shape[0]
+    num = np.abs(a - b).reshape(B, -1).max(axis=1)
+    den = np.abs(b).reshape(B, -1).max(axis=1)
+    return num / den
+
+
 def check_parity(out, ref, exact, label, baseline=False):
     """The parity contract, PER TRAJECTORY, same rule for every shape (no shape-dependent loosening):
 
@@ -119,23 +127,52 @@ def test_waypoint_kernel_matches_oracle(solver, oracle, N, r, K, D, B, variant):
     check_parity(out, ref, exact, f"N={N} r={r} K={K} D={D} variant={variant}", baseline=(N, r, K, D) in BASELINE_SHAPES)
 
 
-def test_generic_kernel_matches_oracle_on_waypoint_mask(solver, oracle):
-    """Waypoint topology with K too large for the shared-memory sweeps (K = 100, the largest size of the
-    reference's timing program, polynomial_timing_evaluation.cpp:117) -> generic banded kernel."""
+@pytest.mark.parametrize("K,B,chunk", [(100, 48, 0), (50, 80, 0), (50, 33, 3), (33, 65, 2), (16, 130, 3), (16, 70, 1),
+                                       (7, 40, 1), (2, 17, 1), (200, 20, 0)])
+def test_large_k_chunked_kernel(solver, oracle, K, B, chunk):
+    """K3: the chunked (checkpoint + recompute) twisted kernel.  K = 50 / 100 are the sizes of the reference's
+    timing program (polynomial_timing_evaluation.cpp:114-129) and tests (test_polynomial_optimization.cpp:822-828);
+    small chunks are forced on small K to exercise every chunk-boundary case (partial outer chunk, chunk = 1,
+    odd / even K, K = 2 with no interior sweep).  Checked against the binary128 solve and the oracle under the
+    check_parity contract, and -- where the resident kernel also runs (K <= 34) -- bitwise against it: the
+    recomputation replays the identical arithmetic."""
     import torch
     import mav_trajectory_generation_b200 as m
-    N, r, K, D, B = 10, 4, 100, 3, 40
+    N, r, D = 10, 4, 3
     pos, times = oracle.make_waypoint_batch(K, D, B, base_seed=106)
-    ref, _ = oracle.solve_waypoint_batch(N, r, pos, times, n_threads=oracle.hardware_threads())
     prob = m.Problem(N, r, K, D)
-    assert prob.kernel == m.KERNEL_GENERIC
+    assert prob.kernel == m.KERNEL_WAYPOINT
     dfix = oracle.waypoint_d_fixed(N, pos)
+    t_d, f_d = torch.from_numpy(times).cuda(), torch.from_numpy(dfix).cuda()
     status = torch.full((B,), -1, dtype=torch.int32, device="cuda")
-    out = solver.solve_linear(prob, torch.from_numpy(times).cuda(), torch.from_numpy(dfix).cuda(), status=status)
-    torch.cuda.synchronize()
+    dfree = torch.zeros((B, D, prob.n_free), dtype=torch.float64, device="cuda")
+    solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, 5)
+    solver.set_option(m.capi.OPT_CHUNK_BLOCKS, chunk)
+    try:
+        out = solver.solve_linear(prob, t_d, f_d, status=status, d_free=dfree)
+        torch.cuda.synchronize()
+    finally:
+        solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, 0)
+        solver.set_option(m.capi.OPT_CHUNK_BLOCKS, 0)
     assert (status.cpu().numpy() == 0).all()
-    exact = oracle.exact_solve_batch(N, r, times, dfix)
-    check_parity(out.cpu().numpy(), ref, exact, "K=100")
+    ref, _ = oracle.solve_waypoint_batch(N, r, pos, times, n_threads=oracle.hardware_threads())
+    exact, exact_free, _ = oracle.exact_solve_batch(N, r, times, dfix, want_free=True)
+    check_parity(out.cpu().numpy(), ref, exact, f"chunked K={K} chunk={chunk}")
+    e_f = np.abs(dfree.cpu().numpy() - exact_free).reshape(B, -1).max(axis=1) / np.abs(exact_free).reshape(B, -1).max(axis=1)
+    if K > 1:
+        assert e_f.max() <= 1e-9, e_f.max()
+    if K <= 34:
+        solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, 3)
+        try:
+            res = solver.solve_linear(prob, t_d, f_d)
+            torch.cuda.synchronize()
+        finally:
+            solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, 0)
+        assert torch.equal(res, out), "chunked kernel differs from the resident kernel"
+    if K >= 50:  # default routing reaches the chunked kernel
+        dflt = solver.solve_linear(prob, t_d, f_d)
+        torch.cuda.synchronize()
+        assert torch.equal(dflt, out) or chunk != 0
 
 
 @pytest.mark.parametrize("N,r,K,D,seed", [(10, 4, 16, 3, 1000), (10, 4, 16, 1, 1003), (10, 3, 5, 3, 110), (10, 2, 5, 3, 109),
@@ -401,6 +438,22 @@ def test_batched_mellinger_gradient(solver, oracle, N, r, K, D, B):
         c_ref, g_ref = oracle.cost_gradient_mellinger(N, r, pos[b], times[b])
         assert abs(cost[b] - c_ref) <= 1e-8 * abs(c_ref)
         assert np.abs(grad[b] - g_ref).max() <= 1e-6 * max(abs(c_ref), np.abs(g_ref).max())
+    # the fused cost-only path evaluates 0.5 d^T H d from the exact tables: against the binary128 cost it is far
+    # tighter than the reference's own c^T Q c arithmetic
+    _, _, c_exact = oracle.exact_solve_batch(N, r, times, oracle.waypoint_d_fixed(N, pos), want_cost=True)
+    assert np.abs(cost - c_exact).max() <= 1e-10 * np.abs(c_exact).max()
+    # and the round-1 path (expand + solve + cost kernels) agrees with it
+    solver.set_option(m.capi.OPT_MELLINGER_UNFUSED, 1)
+    try:
+        cost_u, grad_u = solver.cost_gradient_mellinger(prob, torch.from_numpy(times).cuda(),
+                                                        torch.from_numpy(oracle.waypoint_d_fixed(N, pos)).cuda())
+        torch.cuda.synchronize()
+    finally:
+        solver.set_option(m.capi.OPT_MELLINGER_UNFUSED, 0)
+    cost_u, grad_u = cost_u.cpu().numpy(), grad_u.cpu().numpy()
+    assert np.abs(cost_u - cost).max() <= 1e-8 * np.abs(cost).max()
+    if K > 1:
+        assert np.abs(grad_u - grad).max() <= 1e-6 * max(np.abs(cost).max(), np.abs(grad).max())
 
 
 def test_batched_evaluate(solver, oracle):

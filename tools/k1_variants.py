@@ -19,8 +19,8 @@ def main():
     cfgs = [("C3", 10, 4, 16, 3, 262144), ("C2", 10, 4, 8, 3, 65536), ("C4", 8, 3, 4, 3, 1048576),
             ("C5x1", 10, 4, 16, 3, 1048576), ("odd", 10, 4, 7, 3, 100001)]
     # (variant, ring depth, CTA cap [9 = one CTA per tile], stagger us, dynamic tiles)
-    variants = [(3, 0, 0, 0, 0), (4, 3, 0, 0, 0), (4, 3, 9, 0, 0), (4, 3, 0, 0, 1), (4, 3, 0, 8, 1), (4, 3, 0, 16, 1),
-                (4, 3, 0, 24, 1), (4, 3, 0, 16, 0), (4, 2, 0, 16, 1)]
+    # ring depth "2" selects the ring-depth-3 kernel WITHOUT the hoisted outward-sweep work (A/B of the hoist)
+    variants = [(3, 0, 0, 0, 0), (4, 3, 0, 0, 1), (4, 3, 0, 0, 2), (0, 3, 0, 0, 0)]
     rows = []
     for name, N, r, K, D, B in cfgs:
         prob = m.Problem(N, r, K, D)
@@ -65,7 +65,84 @@ def main():
                        finite=bool(torch.isfinite(out).all().item()), max_rel_diff_vs_v3=diff, dfree_diff=dfd)
             rows.append(row)
             print(json.dumps(row))
+    # ---- large K: the chunked kernel (default routing), and its recompute overhead on the headline shape
+    s.set_option(OPT_DYN, 0)
+    for name, N, r, K, D, B, variant, chunk in (("K50", 10, 4, 50, 3, 65536, 0, 0), ("K50c4", 10, 4, 50, 3, 65536, 5, 4), ("K50c3", 10, 4, 50, 3, 65536, 5, 3), ("K100c4", 10, 4, 100, 3, 32768, 5, 4),
+                                                ("K100", 10, 4, 100, 3, 32768, 0, 0), ("K34", 10, 4, 34, 3, 65536, 0, 0),
+                                                ("K36", 10, 4, 36, 3, 65536, 0, 0),
+                                                ("C3chunk7", 10, 4, 16, 3, 262144, 5, 0), ("C3chunk4", 10, 4, 16, 3, 262144, 5, 4)):
+        prob = m.Problem(N, r, K, D)
+        times, dfix = synth(N, K, D, B, dev)
+        out = torch.zeros((B, K, D, N), device=dev, dtype=torch.float64)
+        st = torch.full((B,), -1, dtype=torch.int32, device=dev)
+        s.set_option(OPT_VARIANT, variant)
+        s.set_option(6, chunk)
+        try:
+            for _ in range(3):
+                s.solve_linear(prob, times, dfix, coeffs=out, status=st)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
+            ev[0].record()
+            for i in range(10):
+                s.solve_linear(prob, times, dfix, coeffs=out)
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(10))
+            med = ms[len(ms) // 2]
+            gbs = B / (med * 1e-3) * prob.bytes_per_trajectory / 1e9
+            row = dict(cfg=name, variant=variant, chunk=chunk, ms=round(med, 4), traj_per_s=round(B / (med * 1e-3)),
+                       frac_hbm=round(gbs / 6575.4, 4), status_ok=bool((st == 0).all().item()),
+                       finite=bool(torch.isfinite(out).all().item()))
+        except Exception as e:
+            row = dict(cfg=name, variant=variant, chunk=chunk, error=str(e))
+        rows.append(row)
+        print(json.dumps(row))
+    s.set_option(6, 0)
     s.set_option(OPT_VARIANT, 0)
+    # ---- arbitrary masks: masked block kernel (0) vs the banded global-scratch kernel (1)
+    import numpy as np
+    for name, N, r, K, D, B in (("gmask16", 10, 4, 16, 3, 65536), ("gmask6_D5", 10, 4, 6, 5, 65536), ("gmaskN12", 12, 5, 8, 3, 32768)):
+        h = N // 2
+        mask = np.zeros((K + 1, h), dtype=np.uint8)
+        mask[:, :2] = 1
+        mask[0, :] = 1
+        mask[-1, :] = 1
+        prob = m.Problem(N, r, K, D, fixed_mask=mask)
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)
+        times = torch.rand((B, K), generator=g, device=dev, dtype=torch.float64) * 4 + 2
+        dfix = torch.rand((B, D, prob.n_fixed), generator=g, device=dev, dtype=torch.float64) * 4 - 2
+        ref = None
+        for gv in (1, 0):
+            s.set_option(7, gv)
+            out = torch.zeros((B, K, D, N), device=dev, dtype=torch.float64)
+            st = torch.full((B,), -1, dtype=torch.int32, device=dev)
+            try:
+                for _ in range(2):
+                    s.solve_linear(prob, times, dfix, coeffs=out, status=st)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    s.solve_linear(prob, times, dfix, coeffs=out)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                gbs = B / (ms * 1e-3) * prob.bytes_per_trajectory / 1e9
+                diff = 0.0
+                if ref is None:
+                    ref = out.clone()
+                else:
+                    den = ref.abs().reshape(B, -1).max(dim=1).values
+                    diff = float(((out - ref).abs().reshape(B, -1).max(dim=1).values / den).max())
+                row = dict(cfg=name, generic_variant=gv, ms=round(ms, 4), traj_per_s=round(B / (ms * 1e-3)),
+                           frac_hbm=round(gbs / 6575.4, 4), status_ok=bool((st == 0).all().item()),
+                           max_rel_diff_vs_banded=diff)
+            except Exception as e:
+                row = dict(cfg=name, generic_variant=gv, error=str(e))
+            rows.append(row)
+            print(json.dumps(row))
+    s.set_option(7, 0)
     s.set_option(OPT_STAG, 0)
     s.set_option(OPT_DYN, 0)
     s.set_option(OPT_CTAS, 0)
