@@ -31,6 +31,8 @@ void unlockHandle();
 // Row-major N x N host matrices built from the exact tables (debug accessors / static helpers).
 void hostMappingMatrix(int N, double T, double* A);
 void hostInverseMappingMatrix(int N, double T, double* Ai);
+// A^-1 of a GIVEN row-major N x N mapping matrix A = [[Lambda, 0], [C, Dm]] (reference linear_impl.h:142-179)
+void hostInvertStructured(int N, const double* A, double* Ai);
 void hostCostMatrix(int N, int derivative, double T, double* Q);
 void hostSegmentHessian(int N, int derivative, double T, double* H);  // A^-T Q A^-1
 

@@ -44,6 +44,22 @@ int orientationDerivativeToInt(const std::string& string);
 
 namespace mav_trajectory_generation {
 
+// Container holding the properties of an extremum: time relative to the segment start, value, segment index
+// (mirror of the reference's include/mav_trajectory_generation/extremum.h:28-45).
+struct Extremum {
+  Extremum() : time(0.0), value(0.0), segment_idx(0) {}
+  Extremum(double _time, double _value, int _segment_idx) : time(_time), value(_value), segment_idx(_segment_idx) {}
+  bool operator<(const Extremum& rhs) const { return value < rhs.value; }
+  bool operator>(const Extremum& rhs) const { return value > rhs.value; }
+  double time;
+  double value;
+  int segment_idx;
+};
+inline std::ostream& operator<<(std::ostream& stream, const Extremum& e) {
+  stream << "time: " << e.time << ", value: " << e.value << ", segment idx: " << e.segment_idx << std::endl;
+  return stream;
+}
+
 class Polynomial {
  public:
   typedef std::vector<Polynomial> Vector;
@@ -80,6 +96,22 @@ class Polynomial {
   void evaluate(double t, Eigen::VectorXd* result) const;
   // One derivative at time t.
   double evaluate(double t, int derivative) const;
+
+  // ---- extrema (reference polynomial.h:151-190, src/polynomial.cpp:27-135).  getRoots returns ALL complex roots of
+  // the given derivative; the reference uses Jenkins-Traub (src/rpoly/rpoly_ak1.cpp), here an Aberth-Ehrlich
+  // simultaneous iteration with real-axis Newton polishing (roots that are real come back with imag() == 0).
+  bool getRoots(int derivative, Eigen::VectorXcd* roots) const;
+  static bool selectMinMaxCandidatesFromRoots(double t_start, double t_end,
+                                              const Eigen::VectorXcd& roots_derivative_of_derivative,
+                                              std::vector<double>* candidates);
+  bool computeMinMaxCandidates(double t_start, double t_end, int derivative, std::vector<double>* candidates) const;
+  bool selectMinMaxFromRoots(double t_start, double t_end, int derivative,
+                             const Eigen::VectorXcd& roots_derivative_of_derivative, std::pair<double, double>* minimum,
+                             std::pair<double, double>* maximum) const;
+  bool computeMinMax(double t_start, double t_end, int derivative, std::pair<double, double>* minimum,
+                     std::pair<double, double>* maximum) const;
+  bool selectMinMaxFromCandidates(const std::vector<double>& candidates, int derivative,
+                                  std::pair<double, double>* minimum, std::pair<double, double>* maximum) const;
 
   bool getPolynomialWithAppendedCoefficients(int new_N, Polynomial* new_polynomial) const;
   // Row of the mapping matrix: d-th derivative basis evaluated at t (reference polynomial.h:201-219).
@@ -201,6 +233,16 @@ class Segment {
 
   Eigen::VectorXd evaluate(double t, int derivative_order = derivative_order::POSITION) const;
 
+  // ---- extrema of the magnitude over a set of dimensions (reference segment.h:84-110, src/segment.cpp:83-180)
+  bool computeMinMaxMagnitudeCandidateTimes(int derivative, double t_start, double t_end,
+                                            const std::vector<int>& dimensions,
+                                            std::vector<double>* candidate_times) const;
+  bool computeMinMaxMagnitudeCandidates(int derivative, double t_start, double t_end,
+                                        const std::vector<int>& dimensions, std::vector<Extremum>* candidates) const;
+  bool selectMinMaxMagnitudeFromCandidates(int derivative, double t_start, double t_end,
+                                           const std::vector<int>& dimensions, const std::vector<Extremum>& candidates,
+                                           Extremum* minimum, Extremum* maximum) const;
+
   bool getSegmentWithSingleDimension(int dimension, Segment* new_segment) const;
   bool getSegmentWithAppendedDimension(const Segment& segment_to_append, Segment* new_segment) const;
   bool offsetSegment(const Eigen::VectorXd& A_r_B);
@@ -269,7 +311,14 @@ class Trajectory {
   // Value of one derivative at time t (clamped into the last segment like the reference,
   // trajectory.cpp:48-79).
   Eigen::VectorXd evaluate(double t, int derivative_order = derivative_order::POSITION) const;
-  // Samples [t_start, t_end] every dt.
+  // ---- extrema / time scaling (reference trajectory.h:126-141, src/trajectory.cpp:191-227, 346-429)
+  bool computeMinMaxMagnitude(int derivative, const std::vector<int>& dimensions, Extremum* minimum,
+                              Extremum* maximum) const;
+  bool computeMaxVelocityAndAcceleration(double* v_max, double* a_max) const;
+  bool scaleSegmentTimes(double scaling);
+  bool scaleSegmentTimesToMeetConstraints(double v_max, double a_max);
+
+  // The reference's sequential sampling walk (src/trajectory.cpp:81-141).
   void evaluateRange(double t_start, double t_end, double dt, int derivative_order,
                      std::vector<Eigen::VectorXd>* result, std::vector<double>* sampling_times = nullptr) const;
 

@@ -25,6 +25,7 @@
 #include <cstddef>
 #include <initializer_list>
 #include <memory>
+#include <complex>
 #include <ostream>
 #include <vector>
 
@@ -228,6 +229,7 @@ std::ostream& operator<<(std::ostream& os, const Matrix<S, R, C>& m) {
 typedef Matrix<double, Dynamic, 1> VectorXd;
 typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
 typedef Matrix<double, 3, 1> Vector3d;
+typedef Matrix<std::complex<double>, Dynamic, 1> VectorXcd;
 
 }  // namespace Eigen
 #endif  // MTG_HAVE_EIGEN

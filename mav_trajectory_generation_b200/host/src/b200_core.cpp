@@ -3,6 +3,7 @@
 // :56-109, :181-260, as flat index arrays), packing/unpacking, and calls into libmtg_b200.so.
 #include "mav_trajectory_generation/b200_core.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -89,6 +90,43 @@ void hostInverseMappingMatrix(int N, double T, double* Ai) {
   for (int j = 0; j < N; ++j)
     for (int s = 0; s < N; ++s) Ai[j * N + s] = (j < h ? A1[j * N + s] : itp[j] * A1[j * N + s] * tp[s % h]);
   // for j < h the scaling T^-j * T^(s mod h) acts on a diagonal (s == j) entry only and cancels
+}
+
+void hostInvertStructured(int N, const double* A, double* Ai) {
+  const int h = N / 2;
+  for (int i = 0; i < N * N; ++i) Ai[i] = 0.0;
+  // Lambda^-1 (the upper-left block is diagonal)
+  for (int k = 0; k < h; ++k) Ai[k * N + k] = 1.0 / A[k * N + k];
+  // Dm^-1 by Gauss-Jordan with partial pivoting on the lower-right h x h block
+  double M[MTG_MAX_N / 2][MTG_MAX_N];
+  for (int i = 0; i < h; ++i)
+    for (int j = 0; j < h; ++j) {
+      M[i][j] = A[(h + i) * N + (h + j)];
+      M[i][h + j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < h; ++c) {
+    int piv = c;
+    for (int i = c + 1; i < h; ++i)
+      if (std::abs(M[i][c]) > std::abs(M[piv][c])) piv = i;
+    if (piv != c)
+      for (int j = 0; j < 2 * h; ++j) std::swap(M[piv][j], M[c][j]);
+    const double ip = 1.0 / M[c][c];
+    for (int j = 0; j < 2 * h; ++j) M[c][j] *= ip;
+    for (int i = 0; i < h; ++i) {
+      if (i == c) continue;
+      const double f = M[i][c];
+      for (int j = 0; j < 2 * h; ++j) M[i][j] -= f * M[c][j];
+    }
+  }
+  for (int i = 0; i < h; ++i)
+    for (int j = 0; j < h; ++j) Ai[(h + i) * N + (h + j)] = M[i][h + j];
+  // lower-left block: -Dm^-1 C Lambda^-1
+  for (int i = 0; i < h; ++i)
+    for (int j = 0; j < h; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < h; ++k) s += M[i][h + k] * A[(h + k) * N + j];
+      Ai[(h + i) * N + j] = -s * Ai[j * N + j];
+    }
 }
 
 void hostCostMatrix(int N, int r, double T, double* Q) {

@@ -6,12 +6,14 @@
 #include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <random>
 #include <string>
 #include <vector>
 
 #include "mav_trajectory_generation/batch_polynomial_optimization.h"
 #include "mav_trajectory_generation/io.h"
 #include "mav_trajectory_generation/polynomial_optimization_linear.h"
+#include "mav_trajectory_generation_ros/ros_conversions.h"
 
 using namespace mav_trajectory_generation;
 
@@ -173,6 +175,150 @@ static void testAMatrixInversion() {
   PolynomialOptimization<N>::computeQuadraticCostJacobian(4, 2.0, &Q);
   EXPECT(Q(3, 3) == 0.0);
   EXPECT_NEAR(Q(4, 4), 2.0 * 24 * 24 * 2.0, 1e-9);  // 2 * B(4,4)^2 * T^1 / 1
+}
+
+// Extrema machinery (reference test_polynomial.cpp / test_polynomial_optimization.cpp extrema cases restated):
+// roots of a polynomial with known roots, min/max against dense sampling, magnitude extrema of a random
+// multi-dimensional segment, time scaling to meet v/a limits, message round trip, evaluateRange conventions.
+static void testExtremaAndConversions() {
+  // p(t) = (t-1)(t-2.5)(t^2+1)(t+3) = expand: roots 1, 2.5, -3, +-i
+  {
+    // (t-1)(t-2.5) = t^2 - 3.5 t + 2.5 ; times (t+3) = t^3 - 0.5 t^2 - 8 t + 7.5 ; times (t^2+1)
+    // = t^5 - 0.5 t^4 - 7 t^3 + 7 t^2 - 8 t + 7.5
+    Eigen::VectorXd c(6);
+    c[0] = 7.5; c[1] = -8.0; c[2] = 7.0; c[3] = -7.0; c[4] = -0.5; c[5] = 1.0;
+    Polynomial p(6, c);
+    Eigen::VectorXcd roots;
+    EXPECT(p.getRoots(0, &roots));
+    EXPECT(roots.size() == 5);
+    int n_real = 0;
+    bool got1 = false, got25 = false, gotm3 = false;
+    for (Eigen::Index i = 0; i < roots.size(); ++i) {
+      if (roots[i].imag() == 0.0) {
+        ++n_real;
+        got1 |= std::abs(roots[i].real() - 1.0) < 1e-12;
+        got25 |= std::abs(roots[i].real() - 2.5) < 1e-12;
+        gotm3 |= std::abs(roots[i].real() + 3.0) < 1e-12;
+      } else {
+        EXPECT_NEAR(std::abs(roots[i].imag()), 1.0, 1e-12);
+        EXPECT_NEAR(roots[i].real(), 0.0, 1e-12);
+      }
+    }
+    EXPECT(n_real == 3 && got1 && got25 && gotm3);
+    // min / max of p on [0, 3] against dense sampling
+    std::pair<double, double> lo, hi;
+    EXPECT(p.computeMinMax(0.0, 3.0, 0, &lo, &hi));
+    double s_lo = 1e300, s_hi = -1e300;
+    for (int k = 0; k <= 300000; ++k) {
+      const double v = p.evaluate(3.0 * k / 300000.0, 0);
+      s_lo = std::min(s_lo, v);
+      s_hi = std::max(s_hi, v);
+    }
+    EXPECT_NEAR(lo.second, s_lo, 1e-8);
+    EXPECT_NEAR(hi.second, s_hi, 1e-8);
+    EXPECT(lo.second <= s_lo + 1e-12 && hi.second >= s_hi - 1e-12);
+  }
+  // random 3-D segments: analytic magnitude extrema of velocity / acceleration bound the sampled ones
+  std::mt19937 rng(7);
+  std::uniform_real_distribution<double> u(-1.0, 1.0);
+  Segment::Vector segs;
+  for (int trial = 0; trial < 5; ++trial) {
+    Segment seg(N, 3);
+    for (int d = 0; d < 3; ++d) {
+      Eigen::VectorXd c(N);
+      double scale = 1.0;
+      for (int j = 0; j < N; ++j) {
+        c[j] = u(rng) * scale;
+        scale *= 0.5;
+      }
+      seg[d].setCoefficients(c);
+    }
+    seg.setTime(2.0 + trial);
+    segs.push_back(seg);
+    for (int der = 1; der <= 2; ++der) {
+      std::vector<double> times;
+      EXPECT(PolynomialOptimization<N>::computeSegmentMaximumMagnitudeCandidates(der, seg, 0.0, seg.getTime(), &times));
+      double best = 0.0;
+      for (double t : times) best = std::max(best, seg.evaluate(t, der).norm());
+      double sampled = 0.0;
+      for (int k = 0; k <= 20000; ++k) sampled = std::max(sampled, seg.evaluate(seg.getTime() * k / 20000.0, der).norm());
+      EXPECT(best >= sampled - 1e-9);
+      EXPECT_NEAR(best, sampled, 1e-6 * (1.0 + sampled));
+    }
+  }
+  Trajectory traj;
+  traj.setSegments(segs);
+  double v_max = 0.0, a_max = 0.0;
+  EXPECT(traj.computeMaxVelocityAndAcceleration(&v_max, &a_max));
+  EXPECT(v_max > 0.0 && a_max > 0.0);
+  Trajectory scaled = traj;
+  EXPECT(scaled.scaleSegmentTimesToMeetConstraints(0.5 * v_max, 0.25 * a_max));
+  double v2 = 0.0, a2 = 0.0;
+  EXPECT(scaled.computeMaxVelocityAndAcceleration(&v2, &a2));
+  EXPECT(v2 <= 0.5 * v_max * 1.001 + 1e-12 && a2 <= 0.25 * a_max * 1.001 + 1e-12);
+  EXPECT(scaled.getMaxTime() > traj.getMaxTime());
+  // the path itself is unchanged by time scaling: same position at the same fraction of every segment
+  {
+    const double f = scaled.getMaxTime() / traj.getMaxTime();
+    for (int k = 0; k <= 10; ++k) {
+      const double t = traj.getMaxTime() * k / 10.0 * 0.999;
+      const Eigen::VectorXd a = traj.evaluate(t, 0), b = scaled.evaluate(t * f, 0);
+      for (int d = 0; d < 3; ++d) EXPECT_NEAR(a[d], b[d], 1e-9);
+    }
+  }
+  // message round trip (3-D and 4-D); 5-D is rejected
+  {
+    mav_planning_msgs::PolynomialTrajectory msg;
+    EXPECT(trajectoryToPolynomialTrajectoryMsg(traj, &msg));
+    EXPECT(msg.segments.size() == segs.size() && msg.segments[0].num_coeffs == N && msg.segments[0].yaw.empty());
+    EXPECT(msg.segments[1].segment_time_ns == segs[1].getTimeNSec());
+    Trajectory back;
+    EXPECT(polynomialTrajectoryMsgToTrajectory(msg, &back));
+    EXPECT(back == traj);
+    Segment s4(N, 4), s5(N, 5);
+    s4.setTime(1.5);
+    s5.setTime(1.5);
+    Trajectory t4, t5;
+    t4.setSegments(Segment::Vector(1, s4));
+    t5.setSegments(Segment::Vector(1, s5));
+    mav_planning_msgs::PolynomialTrajectory4D m4;
+    EXPECT(trajectoryToPolynomialTrajectoryMsg(t4, &m4) && m4.segments[0].yaw.size() == size_t(N));
+    Trajectory b4;
+    EXPECT(polynomialTrajectoryMsgToTrajectory(m4, &b4) && b4.D() == 4);
+    EXPECT(!trajectoryToPolynomialTrajectoryMsg(t5, &msg) && msg.segments.empty());
+  }
+  // evaluateRange follows the reference's walk: t_end is excluded, the clock starts at the start of the segment
+  // that contains t_start, a start beyond the end yields nothing
+  {
+    std::vector<Eigen::VectorXd> out;
+    std::vector<double> st;
+    traj.evaluateRange(0.0, 1.0, 0.25, 0, &out, &st);
+    EXPECT(out.size() == 4 && st.size() == 4 && st[3] == 0.75);
+    traj.evaluateRange(traj.getMaxTime() + 1.0, traj.getMaxTime() + 2.0, 0.1, 0, &out, &st);
+    EXPECT(out.empty());
+    const double t0 = segs[0].getTime() + 0.5;  // inside segment 1: the sample clock starts at segs[0].getTime()
+    traj.evaluateRange(t0, t0 + 1.0, 0.5, 0, &out, &st);
+    EXPECT(!st.empty() && st[0] == segs[0].getTime());
+    const Eigen::VectorXd direct = traj.evaluate(t0, 0);
+    for (int d = 0; d < 3; ++d) EXPECT_NEAR(out[0][d], direct[d], 1e-12);
+  }
+  // invertMappingMatrix inverts the matrix it is given (a mapping matrix with a perturbed lower block)
+  {
+    PolynomialOptimization<N>::SquareMatrix A, Ai;
+    PolynomialOptimization<N>::setupMappingMatrix(2.0, &A);
+    for (int i = N / 2; i < N; ++i)
+      for (int j = 0; j < N; ++j) A(i, j) *= 1.0 + 0.01 * ((i * 7 + j * 3) % 5);
+    PolynomialOptimization<N>::invertMappingMatrix(A, &Ai);
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0, mag = 0.0;
+        for (int k = 0; k < N; ++k) {
+          s += A(i, k) * Ai(k, j);
+          mag += std::abs(A(i, k) * Ai(k, j));
+        }
+        EXPECT_NEAR(s, i == j ? 1.0 : 0.0, 1e-11 * (1.0 + mag));
+      }
+  }
 }
 
 static void testLayoutOnly() {
@@ -380,6 +526,7 @@ int main(int argc, char** argv) {
   testAMatrixInversion();
   testLayoutOnly();
   testYamlIo();
+  testExtremaAndConversions();
   if (!cpu_only) {
     testTwoVerticesSetup();
     testReadmeExample();
