@@ -285,6 +285,43 @@ def measure_config(torch, m, solver, name, N, r, K, D, B, dev, peak, steps=20, m
         return {"workload": name, "failed": str(e)}
 
 
+def widened_rows(torch, m, solver, dev, peak):
+    """SURVEY.md 8f rows built past the hot path, each with its own throughput: batched Mellinger gradient (fused
+    cost-only pass vs the round-1 expand + solve + cost kernels) and batched evaluateRange / sampling."""
+    out = {}
+    try:
+        N, r, K, D, B = 10, 4, 16, 3, 32768
+        prob = m.Problem(N, r, K, D)
+        _, times, dfix = synth_batch(torch, N, K, D, B, dev, seed=11)
+        res = {}
+        for name, flag in (("fused_cost_only", 0), ("expand_solve_cost_kernels", 1)):
+            solver.set_option(m.capi.OPT_MELLINGER_UNFUSED, flag)
+            ms = _time_launches(torch, lambda: solver.cost_gradient_mellinger(prob, times, dfix), 5, warmup=2)
+            res[name] = {"gradients_per_s": B / (ms * 1e-3), "solves_per_s": B * (K + 1) / (ms * 1e-3), "ms": ms}
+        solver.set_option(m.capi.OPT_MELLINGER_UNFUSED, 0)
+        res["workload"] = f"getCostAndGradientMellinger for {B} trajectories, C3 shape ({K + 1} re-solves each)"
+        out["mellinger_gradient"] = res
+    except Exception as e:
+        out["mellinger_gradient"] = {"failed": str(e)}
+    try:
+        N, r, K, D, B, S = 10, 4, 16, 3, 65536, 128
+        prob = m.Problem(N, r, K, D)
+        _, times, dfix = synth_batch(torch, N, K, D, B, dev, seed=12)
+        coeffs = solver.solve_linear(prob, times, dfix)
+        t_end = float(times.sum(dim=1).min().item())
+        dt = t_end / (S - 2)
+        ms = _time_launches(torch, lambda: solver.evaluate_range(times, coeffs, 0.0, t_end, dt, derivs=(0, 1, 2, 3, 4),
+                                                                 max_samples=S), 5, warmup=2)
+        nbytes = B * (8 * K + 8 * K * D * N + 8 * S * 5 * D + 4)
+        out["evaluate_range"] = {"workload": f"sampleTrajectoryInRange sample set (derivatives 0..4) of {B} C3 trajectories, "
+                                             f"{S} samples each", "ms": ms, "samples_per_s": B * (S - 1) / (ms * 1e-3),
+                                 "achieved_GBps": nbytes / (ms * 1e-3) / 1e9,
+                                 "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak}
+    except Exception as e:
+        out["evaluate_range"] = {"failed": str(e)}
+    return out
+
+
 def b1_latency(torch, m, solver, dev):
     """PolynomialOptimization<N>::solveLinear() on ONE object = a B=1 call (C1 shape; every nlopt callback,
     reference nonlinear_impl.h:569-570).  Wall-clock per call including the synchronisation the caller needs."""
@@ -513,6 +550,7 @@ def run_ours(args):
                                                         10, 4, 16, 3, 65536, dev, peak,
                                                         mask=np.array(gmask, dtype=np.uint8), steps=5)
                 extras["b1_latency"] = b1_latency(torch, m, solver, dev)
+                extras.update(widened_rows(torch, m, solver, dev, peak))
                 line["configs"] = extras
             if not args.no_cpu_baseline:
                 try:

@@ -193,6 +193,14 @@ int mtg_coeffs_from_constraints_batch_host_f64(mtg_handle* h, const mtg_problem*
 int mtg_compute_cost_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
                                     const double* coeffs, double* cost);
 
+/* host-pointer variants of the two widened entry points (single stream: copy in, kernels, copy out) */
+int mtg_cost_gradient_mellinger_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                                               const double* d_fixed, double* cost, double* grad);
+int mtg_evaluate_range_batch_host_f64(mtg_handle* h, int32_t N, int32_t K, int32_t D, int64_t B, const double* seg_times,
+                                      const double* coeffs, double t_start, double t_end, double dt, int32_t n_derivs,
+                                      const int32_t* derivs, int32_t max_samples, double* out, int32_t* n_samples,
+                                      double* sampling_times);
+
 /* ---- memory helpers (so host code above the ABI needs no CUDA headers) -------------------- */
 void* mtg_host_alloc(mtg_handle* h, uint64_t bytes);   /* pinned */
 void mtg_host_free(mtg_handle* h, void* ptr);

@@ -590,14 +590,10 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
   // cudaGetLastError() after our launches must report OUR launch only
   (void)cudaGetLastError();
   int kind = backsub_only ? MTG_KERNEL_NOFREE : route(h, p, L);
-  // The TMA tensor stores of the TMEM / chunked kernels need a 16-byte aligned output; an 8-byte aligned caller
-  // buffer (e.g. a tensor slice) takes the shared-memory twisted kernel when its state fits, else the generic one.
+  // Every specialised kernel stores coefficients in 16-byte units (TMA tensor stores / double2): an output that
+  // is only 8-byte aligned (e.g. a tensor slice) takes the banded generic kernel, which stores scalar doubles.
   const bool out_aligned = (reinterpret_cast<uintptr_t>(coeffs) & 15u) == 0;
-  if (kind == MTG_KERNEL_WAYPOINT && !fused) {
-    const WaypointEntry* e0 = find_waypoint(h, p, L);
-    const bool twisted_fits = size_t((p->K + 1) / 2 - 1) * e0->slots * 32 * sizeof(double) <= h->smem_optin;
-    if (!out_aligned && !twisted_fits) kind = MTG_KERNEL_GENERIC;
-  }
+  if (kind == MTG_KERNEL_WAYPOINT && !fused && !out_aligned) kind = MTG_KERNEL_GENERIC;
   if (kind == MTG_KERNEL_WAYPOINT) {
     const WaypointEntry* e = find_waypoint(h, p, L);
     mtg::WaypointParams prm;
@@ -1395,6 +1391,70 @@ int mtg_compute_cost_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t
                                   reinterpret_cast<double*>(base + o_cost), s);
   if (rc != MTG_OK) return rc;
   MTG_CUDA(h, cudaMemcpyAsync(cost, base + o_cost, 8 * B, cudaMemcpyDeviceToHost, s));
+  MTG_CUDA(h, cudaStreamSynchronize(s));
+  return MTG_OK;
+}
+
+int mtg_cost_gradient_mellinger_batch_host_f64(mtg_handle* h, const mtg_problem* p, int64_t B, const double* seg_times,
+                                               const double* d_fixed, double* cost, double* grad) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  if (!valid_problem(p) || B < 0 || (B > 0 && (!seg_times || !d_fixed || !grad))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  if (B == 0) return MTG_OK;
+  DeviceGuard g(h->device);
+  CachedTopology* topo = get_topology(h, p);
+  if (!topo) return MTG_ERR_CUDA;
+  const size_t K = p->K, D = p->D, nf = topo->layout.n_fixed;
+  const size_t o_f = align_up(K * 8 * B), o_c = align_up(o_f + D * nf * 8 * B), o_g = align_up(o_c + 8 * B);
+  int rc = ensure_pipe(h, 0, o_g + K * 8 * B);
+  if (rc != MTG_OK) return rc;
+  cudaStream_t s = h->streams[0];
+  char* base = static_cast<char*>(h->dev_buf[0]);
+  PipeSyncGuard sync_on_exit{h};
+  MTG_CUDA(h, cudaMemcpyAsync(base, seg_times, K * 8 * B, cudaMemcpyHostToDevice, s));
+  MTG_CUDA(h, cudaMemcpyAsync(base + o_f, d_fixed, D * nf * 8 * B, cudaMemcpyHostToDevice, s));
+  rc = mtg_cost_gradient_mellinger_batch_f64(h, p, B, reinterpret_cast<double*>(base), reinterpret_cast<double*>(base + o_f),
+                                             reinterpret_cast<double*>(base + o_c), reinterpret_cast<double*>(base + o_g), s);
+  if (rc != MTG_OK) return rc;
+  if (cost) MTG_CUDA(h, cudaMemcpyAsync(cost, base + o_c, 8 * B, cudaMemcpyDeviceToHost, s));
+  MTG_CUDA(h, cudaMemcpyAsync(grad, base + o_g, K * 8 * B, cudaMemcpyDeviceToHost, s));
+  MTG_CUDA(h, cudaStreamSynchronize(s));
+  return MTG_OK;
+}
+
+int mtg_evaluate_range_batch_host_f64(mtg_handle* h, int32_t N, int32_t K, int32_t D, int64_t B, const double* seg_times,
+                                      const double* coeffs, double t_start, double t_end, double dt, int32_t n_derivs,
+                                      const int32_t* derivs, int32_t max_samples, double* out, int32_t* n_samples,
+                                      double* sampling_times) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  if (N < 1 || N > MTG_MAX_N || K < 1 || D < 1 || B < 0 || n_derivs < 1 || n_derivs > 8 || max_samples < 0 ||
+      (B > 0 && (!seg_times || !coeffs || !n_samples || (max_samples > 0 && !out)))) {
+    h->error = "bad argument";
+    return MTG_ERR_BAD_ARG;
+  }
+  if (B == 0) return MTG_OK;
+  DeviceGuard g(h->device);
+  const size_t b_t = size_t(K) * 8 * B, b_c = size_t(K) * D * N * 8 * B, b_o = size_t(max_samples) * n_derivs * D * 8 * B,
+               b_n = 4 * size_t(B), b_s = size_t(max_samples) * 8 * B;
+  const size_t o_c = align_up(b_t), o_o = align_up(o_c + b_c), o_n = align_up(o_o + b_o), o_s = align_up(o_n + b_n);
+  int rc = ensure_pipe(h, 0, o_s + b_s);
+  if (rc != MTG_OK) return rc;
+  cudaStream_t s = h->streams[0];
+  char* base = static_cast<char*>(h->dev_buf[0]);
+  PipeSyncGuard sync_on_exit{h};
+  MTG_CUDA(h, cudaMemcpyAsync(base, seg_times, b_t, cudaMemcpyHostToDevice, s));
+  MTG_CUDA(h, cudaMemcpyAsync(base + o_c, coeffs, b_c, cudaMemcpyHostToDevice, s));
+  rc = mtg_evaluate_range_batch_f64(h, N, K, D, B, reinterpret_cast<double*>(base), reinterpret_cast<double*>(base + o_c),
+                                    t_start, t_end, dt, n_derivs, derivs, max_samples, reinterpret_cast<double*>(base + o_o),
+                                    reinterpret_cast<int32_t*>(base + o_n),
+                                    sampling_times ? reinterpret_cast<double*>(base + o_s) : nullptr, s);
+  if (rc != MTG_OK) return rc;
+  if (max_samples > 0) MTG_CUDA(h, cudaMemcpyAsync(out, base + o_o, b_o, cudaMemcpyDeviceToHost, s));
+  MTG_CUDA(h, cudaMemcpyAsync(n_samples, base + o_n, b_n, cudaMemcpyDeviceToHost, s));
+  if (sampling_times && max_samples > 0)
+    MTG_CUDA(h, cudaMemcpyAsync(sampling_times, base + o_s, b_s, cudaMemcpyDeviceToHost, s));
   MTG_CUDA(h, cudaStreamSynchronize(s));
   return MTG_OK;
 }

@@ -92,6 +92,12 @@ class BatchCore {
   bool solveWaypointsNfabian(size_t B, size_t K, const double* positions, int r, double v_max, double a_max,
                              double magic);
   std::vector<double> computeCosts() const;
+  // batched getCostAndGradientMellinger at the current segment times (grad: [B][K])
+  void costGradientMellinger(std::vector<double>* cost, std::vector<double>* grad) const;
+  // batched Trajectory::evaluateRange of the solved trajectories (samples: [B][max_samples][n_derivs][D])
+  void evaluateRange(double t_start, double t_end, double dt, const std::vector<int>& derivatives, int max_samples,
+                     std::vector<double>* samples, std::vector<int32_t>* n_samples,
+                     std::vector<double>* sampling_times) const;
   void getSegments(size_t b, Segment::Vector* segments) const;
 
   int N_;

@@ -63,6 +63,21 @@ class BatchPolynomialOptimization {
   const double* freeConstraints() const { return core_.d_free_; }  // [B][D][n_free]
   const int32_t* status() const { return core_.status_; }
   std::vector<double> computeCosts() const { return core_.computeCosts(); }
+  // PolynomialOptimizationNonLinear::getCostAndGradientMellinger (reference
+  // impl/polynomial_optimization_nonlinear_impl.h:286-364) for every problem of the batch at its current segment
+  // times: cost[b] and grad[b*K + n], the K+1 re-solves per problem fused into one cost-only device pass.
+  void costGradientMellinger(std::vector<double>* cost, std::vector<double>* grad) const {
+    core_.costGradientMellinger(cost, grad);
+  }
+  // Trajectory::evaluateRange (reference src/trajectory.cpp:81-141) of every solved trajectory;
+  // derivatives = {0,1,2,3,4} gives the sample set of sampleTrajectoryInRange (src/trajectory_sampling.cpp:45-110).
+  // samples[((b*max_samples + s)*n_derivs + q)*D + dim], n_samples[b] as the reference would produce (-1: t_start
+  // beyond the trajectory).
+  void evaluateRange(double t_start, double t_end, double dt, const std::vector<int>& derivatives, int max_samples,
+                     std::vector<double>* samples, std::vector<int32_t>* n_samples,
+                     std::vector<double>* sampling_times = nullptr) const {
+    core_.evaluateRange(t_start, t_end, dt, derivatives, max_samples, samples, n_samples, sampling_times);
+  }
 
  private:
   b200::BatchCore core_;

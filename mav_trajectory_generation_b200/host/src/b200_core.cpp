@@ -538,6 +538,35 @@ std::vector<double> BatchCore::computeCosts() const {
   return cost;
 }
 
+void BatchCore::costGradientMellinger(std::vector<double>* cost, std::vector<double>* grad) const {
+  CHECK_NOTNULL(grad)->assign(B_ * size_t(topo_.K), 0.0);
+  if (cost) cost->assign(B_, 0.0);
+  mtg_problem p = {N_, topo_.r, topo_.K, topo_.D, topo_.mask.data()};
+  HandleLock lock;
+  mtg_handle* h = defaultHandle();
+  const int rc = mtg_cost_gradient_mellinger_batch_host_f64(h, &p, static_cast<int64_t>(B_), times_, d_fixed_,
+                                                            cost ? cost->data() : nullptr, grad->data());
+  CHECK_EQ(rc, MTG_OK) << mtg_last_error(h);
+}
+
+void BatchCore::evaluateRange(double t_start, double t_end, double dt, const std::vector<int>& derivatives,
+                              int max_samples, std::vector<double>* samples, std::vector<int32_t>* n_samples,
+                              std::vector<double>* sampling_times) const {
+  CHECK(!derivatives.empty() && derivatives.size() <= 8);
+  CHECK_GT(dt, 0.0);
+  CHECK_NOTNULL(samples)->assign(B_ * size_t(max_samples) * derivatives.size() * topo_.D, 0.0);
+  CHECK_NOTNULL(n_samples)->assign(B_, 0);
+  if (sampling_times) sampling_times->assign(B_ * size_t(max_samples), 0.0);
+  std::vector<int32_t> ders(derivatives.begin(), derivatives.end());
+  HandleLock lock;
+  mtg_handle* h = defaultHandle();
+  const int rc = mtg_evaluate_range_batch_host_f64(h, N_, topo_.K, topo_.D, static_cast<int64_t>(B_), times_, coeffs_,
+                                                   t_start, t_end, dt, static_cast<int32_t>(ders.size()), ders.data(),
+                                                   max_samples, samples->data(), n_samples->data(),
+                                                   sampling_times ? sampling_times->data() : nullptr);
+  CHECK_EQ(rc, MTG_OK) << mtg_last_error(h);
+}
+
 void BatchCore::getSegments(size_t b, Segment::Vector* segments) const {
   CHECK_LT(b, B_);
   unpackSegments(topo_, coeffs_ + b * size_t(topo_.K) * topo_.D * N_, times_ + b * topo_.K, segments);

@@ -492,6 +492,59 @@ static void testBatchMatchesSingle() {
 }
 
 // Fused time allocation + solve equals estimateSegmentTimes() on the host followed by the batch solve.
+// Batch widenings against the single-object mirror: Mellinger gradient = finite differences of computeCost() over
+// re-solved objects (reference nonlinear_impl.h:286-364); evaluateRange == Trajectory::evaluateRange bit for bit.
+static void testBatchMellingerAndRange() {
+  const int K = 5, D = 3, B = 9;
+  std::vector<Vertex::Vector> all_v;
+  std::vector<std::vector<double> > all_t;
+  for (int b = 0; b < B; ++b) {
+    Eigen::VectorXd lo = Eigen::VectorXd::Constant(D, -10.0), hi = Eigen::VectorXd::Constant(D, 10.0);
+    Vertex::Vector v = createRandomVertices(getHighestDerivativeFromN(N), K, lo, hi, 500 + b);
+    all_t.push_back(estimateSegmentTimes(v, 3.0, 5.0));
+    all_v.push_back(v);
+  }
+  BatchPolynomialOptimization<N> batch(D);
+  batch.setupFromVertices(all_v, all_t, 4);
+  batch.solveLinear();
+  std::vector<double> cost, grad;
+  batch.costGradientMellinger(&cost, &grad);
+  for (int b = 0; b < B; ++b) {
+    PolynomialOptimization<N> opt(D);
+    opt.setupFromVertices(all_v[b], all_t[b], 4);
+    opt.solveLinear();
+    const double J = opt.computeCost();
+    EXPECT_NEAR(cost[b], J, 1e-8 * std::abs(J));
+    for (int n = 0; n < K; ++n) {
+      std::vector<double> t = all_t[b];
+      for (int i = 0; i < K; ++i) t[i] = std::max(0.1, i == n ? t[i] + 0.1 : t[i] - 0.1 / (K - 1.0));
+      opt.updateSegmentTimes(t);
+      opt.solveLinear();
+      const double g = (opt.computeCost() - J) / 0.1;
+      EXPECT_NEAR(grad[b * K + n], g, 1e-6 * std::max(std::abs(J), std::abs(g)));
+    }
+  }
+  const std::vector<int> ders = {0, 1, 2, 3, 4};
+  const int S = 64;
+  std::vector<double> samples, st;
+  std::vector<int32_t> ns;
+  batch.evaluateRange(0.7, 9.0, 0.2, ders, S, &samples, &ns, &st);
+  for (int b = 0; b < B; ++b) {
+    Trajectory traj;
+    batch.getTrajectory(b, &traj);
+    for (size_t q = 0; q < ders.size(); ++q) {
+      std::vector<Eigen::VectorXd> ref;
+      std::vector<double> ref_t;
+      traj.evaluateRange(0.7, 9.0, 0.2, ders[q], &ref, &ref_t);
+      EXPECT(ns[b] == static_cast<int32_t>(ref.size()));
+      for (size_t k = 0; k < ref.size() && k < size_t(S); ++k) {
+        EXPECT(st[b * S + k] == ref_t[k]);
+        for (int d = 0; d < D; ++d) EXPECT(samples[((size_t(b) * S + k) * ders.size() + q) * D + d] == ref[k][d]);
+      }
+    }
+  }
+}
+
 static void testFusedWaypointSolve() {
   const int D = 3, K = 6, B = 19;
   Eigen::VectorXd lo = Eigen::VectorXd::Constant(D, -10.0), hi = Eigen::VectorXd::Constant(D, 10.0);
@@ -534,6 +587,7 @@ int main(int argc, char** argv) {
     for (const Params& p : kParams) testConstraintPacking(p);
     testBatchMatchesSingle();
     testFusedWaypointSolve();
+    testBatchMellingerAndRange();
   }
   std::printf("%s: %d checks, %d failures\n", cpu_only ? "cpu-only" : "full", g_checks, g_failures);
   return g_failures == 0 ? 0 : 1;

@@ -584,7 +584,7 @@ def test_nfabian_host_pipeline_pack_fallback_bitwise(solver, oracle, N, r, K, D,
 def test_mellinger_odd_offsets_and_unaligned_output(solver, oracle):
     """(10,4,16,3) with B = 33 put the expanded coefficient buffer at an odd double offset (TMA
     tensor maps need 16 bytes) -> MTG_ERR_CUDA.  Sub-buffers are now 256-byte aligned; and a caller buffer that
-    is only 8-byte aligned takes the shared-memory kernel instead of failing."""
+    is only 8-byte aligned takes the scalar-store generic kernel instead of failing."""
     import torch
     import mav_trajectory_generation_b200 as m
     N, r, K, D, B = 10, 4, 16, 3, 33
