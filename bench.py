@@ -369,6 +369,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the scatter/gather path is point-to-point: let NCCL spread every send/recv over many channels
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=dev)
 
     N, r, K, D, total = CONFIGS[args.config]

@@ -383,7 +383,7 @@ int launch_chunked(mtg_handle* h, const mtg_problem* p, const WaypointEntry* e, 
   const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
   auto smem_of = [&](int C, int ntm) {
     return size_t(mtg::kTmemHeaderBytes) + size_t(4) * e->stage_bytes_per_warp +
-           size_t(rd * (1 + D) + (C + 1) + (D + 1) + (1 + 2 * D) + (C - ntm) * kslots) * mtg::kTmemThreads * 8;
+           size_t(rd * (1 + D) + (C + 1) + (D + 1) + (1 + 2 * D) + kck + (C - ntm) * kslots) * mtg::kTmemThreads * 8;
   };
   int best_ctas = 0, best_C = 0, best_cols = 0, best_ntm = 0;
   size_t best_smem = 0;
