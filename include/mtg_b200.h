@@ -98,7 +98,8 @@ int mtg_device_is_sm100(const mtg_handle* h);
  *                             1 = one thread per trajectory, 2 = twisted (state in shared memory),
  *                             3 = twisted with the sweep state in tensor memory + TMA tensor stores,
  *                             4 = persistent version of 3 with deep input prefetch,
- *                             5 = chunked (checkpoint + recompute) kernel, any K (default for K too large for 3). */
+ *                             5 = chunked (checkpoint + recompute) kernel, any K (default for K too large for 3),
+ *                             6 = 4 with the inputs moved by TMA bulk copies (K <= 8, B % 16 == 0, aligned inputs). */
 #define MTG_OPT_WAYPOINT_VARIANT 1
 #define MTG_OPT_RING_DEPTH 2      /* reserved (the persistent kernel is built with a 3-deep input ring) */
 #define MTG_OPT_CTAS_PER_SM 3     /* persistent kernel: cap on resident CTAs per SM, 0 = as many as fit, 9 = one CTA per tile */
@@ -106,6 +107,7 @@ int mtg_device_is_sm100(const mtg_handle* h);
 #define MTG_OPT_CHUNK_BLOCKS 6    /* chunked (large-K) kernel: resident vertex blocks per lane, 0 = auto */
 #define MTG_OPT_GENERIC_VARIANT 7 /* arbitrary masks: 0 = masked block kernel (default), 1 = banded kernel in global scratch */
 #define MTG_OPT_MELLINGER_UNFUSED 8 /* 1 = batched Mellinger gradient through expand + solve + cost kernels */
+#define MTG_OPT_TMA_INPUTS 9      /* K <= 8: 1 = prefer the kernel that moves whole input tiles with TMA bulk copies */
 #define MTG_OPT_DYNAMIC_TILES 5   /* persistent kernel: warps draw tiles from a global counter: 0 = auto, 1 = always, 2 = never */
 int mtg_set_option(mtg_handle* h, int key, int value);
 

@@ -16,6 +16,7 @@
 #include "mtg_twisted_tmem_kernel.cuh"
 #include "mtg_twisted_tmem_v4_kernel.cuh"
 #include "mtg_twisted_chunked_kernel.cuh"
+#include "mtg_twisted_tmem_v5_kernel.cuh"
 #include "mtg_masked_block_kernel.cuh"
 #include "mtg_waypoint_kernel.cuh"
 
@@ -51,6 +52,7 @@ struct mtg_handle {
   int ring_depth = 3;        // MTG_OPT_RING_DEPTH (v4 kernel: cp.async input ring buffers, 2..4)
   int ctas_per_sm = 0;       // MTG_OPT_CTAS_PER_SM (v4 kernel: 0 = as many as fit, 9 = one CTA per tile, not persistent)
   int stagger_us = 0;        // MTG_OPT_STAGGER_US (v4 kernel: CTA start times spread over this many microseconds)
+  int tma_inputs = 0;        // MTG_OPT_TMA_INPUTS (default routing prefers the TMA-input kernel v5 when eligible)
   int mellinger_unfused = 0; // MTG_OPT_MELLINGER_UNFUSED (1 = expand + solve + cost kernels, the round-1 path)
   int generic_variant = 0;   // MTG_OPT_GENERIC_VARIANT (0 = masked block kernel, 1 = banded kernel in global scratch)
   int chunk_blocks = 0;      // MTG_OPT_CHUNK_BLOCKS (chunked kernel: resident vertex blocks per lane, 0 = auto)
@@ -233,6 +235,22 @@ const V4Entry kV4Kernels[] = {MTG_V4(10, 4, 3, 2), MTG_V4(8, 3, 3, 3), MTG_V4(10
                               MTG_V4(10, 2, 3, 2), MTG_V4(12, 5, 3, 2)};
 constexpr int kV4MaxK = 8;
 
+// ---- v5: v4 with the inputs moved by TMA bulk copies (whole 16-trajectory tiles, double buffered); K <= 8
+typedef void (*V5Kernel)(const mtg::WaypointParams, const mtg::TmemLaunchV5, const CUtensorMap);
+struct V5Entry {
+  int N, R, D;
+  V5Kernel fn;
+};
+const V5Entry kV5Kernels[] = {{10, 4, 3, mtg::twisted_tmem_v5_kernel<10, 4, 3, 2>},
+                              {8, 3, 3, mtg::twisted_tmem_v5_kernel<8, 3, 3, 3>},
+                              {10, 4, 1, mtg::twisted_tmem_v5_kernel<10, 4, 1, 2>},
+                              {10, 3, 3, mtg::twisted_tmem_v5_kernel<10, 3, 3, 2>}};
+const V5Entry* find_v5(const mtg_problem* p) {
+  for (const auto& e : kV5Kernels)
+    if (e.N == p->N && e.R == p->r && e.D == p->D) return &e;
+  return nullptr;
+}
+
 const V4Entry* find_v4(const mtg_problem* p) {
   for (const auto& e : kV4Kernels)
     if (e.N == p->N && e.R == p->r && e.D == p->D) return &e;
@@ -383,7 +401,7 @@ int launch_chunked(mtg_handle* h, const mtg_problem* p, const WaypointEntry* e, 
   const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
   auto smem_of = [&](int C, int ntm) {
     return size_t(mtg::kTmemHeaderBytes) + size_t(4) * e->stage_bytes_per_warp +
-           size_t(rd * (1 + D) + (C + 1) + (D + 1) + (1 + 2 * D) + kck + (C - ntm) * kslots) * mtg::kTmemThreads * 8;
+           size_t(rd * (1 + D) + (C + 1) + (D + 1) + (1 + 2 * D) + (C - ntm) * kslots) * mtg::kTmemThreads * 8;
   };
   int best_ctas = 0, best_C = 0, best_cols = 0, best_ntm = 0;
   size_t best_smem = 0;
@@ -620,6 +638,64 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
     const bool coeffs_aligned = (reinterpret_cast<uintptr_t>(coeffs) & 15u) == 0;
     if (h->waypoint_variant == 5 && coeffs_aligned && !fused)
       return launch_chunked(h, p, e, prm, coeffs, B, stream, slot);
+    const bool v5_eligible = !fused && coeffs_aligned && p->K <= kV4MaxK && (B % 16) == 0 &&
+                             ((reinterpret_cast<uintptr_t>(times) | reinterpret_cast<uintptr_t>(dfix)) & 15u) == 0;
+    if ((h->waypoint_variant == 6 || (h->waypoint_variant == 0 && h->tma_inputs)) && v5_eligible) {
+      const V5Entry* e5 = find_v5(p);
+      if (e5) {
+        const int hh = p->N / 2, mm = hh - 1;
+        const int kslots = mm * (mm + 1) / 2 + mm * p->D + p->D;
+        const int nmax = (p->K + 1) / 2 - 1;
+        cudaFuncAttributes attr;
+        MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)e5->fn));
+        const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
+        int best_ctas = 0, best_cols = 0, best_ntm = 0;
+        size_t best_smem = 0;
+        const int col_options[] = {256, 128, 64, 32, 512};
+        for (int cols : col_options) {
+          const int ntm = std::min(nmax, cols / (2 * kslots));
+          if (ntm == 0 && nmax > 0) continue;
+          const int spill = std::max(0, nmax - ntm) * kslots;
+          const size_t smem = mtg::kTmemHeaderBytes + size_t(4) * e->stage_bytes_per_warp + 128 +
+                              size_t(4) * 2 * 16 * size_t(p->K + p->D * L.n_fixed) * 8 + size_t(spill) * mtg::kTmemThreads * 8;
+          if (smem > h->smem_optin) continue;
+          int ctas = std::min<int>(by_regs, int((228 * 1024) / (smem + 1024)));
+          ctas = std::min(std::min(ctas, 512 / cols), 8);
+          if (ctas > best_ctas || (ctas == best_ctas && smem < best_smem)) {
+            best_ctas = ctas;
+            best_cols = cols;
+            best_ntm = ntm;
+            best_smem = smem;
+          }
+        }
+        if (best_ctas >= 2) {
+          mtg::TmemLaunchV5 tl;
+          tl.n_tmem_blocks = best_ntm;
+          tl.tmem_cols = best_cols;
+          tl.tile_counter = nullptr;
+          const int64_t blocks = std::min<int64_t>((B + 63) / 64, int64_t(best_ctas) * h->sm_count);
+          const int64_t tiles_per_warp = (B / 16) / std::max<int64_t>(1, blocks * 4);
+          if (h->dynamic_tiles == 1 || (h->dynamic_tiles == 0 && tiles_per_warp >= 16)) {
+            if (!h->tile_counters) MTG_CUDA(h, cudaMalloc(&h->tile_counters, sizeof(unsigned long long) * 32 * (mtg_handle::kPipe + 1)));
+            tl.tile_counter = h->tile_counters + 32 * slot;
+            MTG_CUDA(h, cudaMemsetAsync(tl.tile_counter, 0, sizeof(unsigned long long), stream));
+          }
+          {
+            const int rc_smem = ensure_dyn_smem(h, (const void*)e5->fn, best_smem);
+            if (rc_smem != MTG_OK) return rc_smem;
+          }
+          CUtensorMap tmap;
+          {
+            const int rc = encode_coeff_tmap(h, &tmap, coeffs, B, p);
+            if (rc != MTG_OK) return rc;
+          }
+          e5->fn<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl, tmap);
+          MTG_CUDA(h, cudaGetLastError());
+          h->launches++;
+          return MTG_OK;
+        }
+      }
+    }
     if ((h->waypoint_variant == 4 || (h->waypoint_variant == 0 && p->K <= kV4MaxK)) && coeffs_aligned) {
       const V4Entry* e4 = find_v4(p);
       if (e4) {
@@ -924,7 +1000,11 @@ int mtg_set_option(mtg_handle* h, int key, int value) {
     h->chunk_blocks = value;
     return MTG_OK;
   }
-  if (key == MTG_OPT_WAYPOINT_VARIANT && value >= 0 && value <= 5) {
+  if (key == MTG_OPT_TMA_INPUTS && (value == 0 || value == 1)) {
+    h->tma_inputs = value;
+    return MTG_OK;
+  }
+  if (key == MTG_OPT_WAYPOINT_VARIANT && value >= 0 && value <= 6) {
     h->waypoint_variant = value;
     return MTG_OK;
   }

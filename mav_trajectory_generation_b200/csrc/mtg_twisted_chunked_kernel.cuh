@@ -20,6 +20,11 @@
 // CTAs are persistent (static tile assignment) so that the checkpoint area is bounded by the number of resident
 // threads, not by the batch.  Arithmetic per vertex is exactly the v3/v4 sequence: results are bitwise equal to
 // the headline kernels where both run (tests force tiny chunks on K = 16 to prove it).
+//
+// Measured and rejected (profiles/r02_k1_variants.json): staging the next round's checkpoint and restart inputs in
+// shared memory with cp.async during the current round's back-substitution (K = 50: 0.352 vs 0.383 of the HBM
+// roofline, K = 100: 0.294 vs 0.337) -- the extra 28 KB of shared memory per CTA shrink the L1 that serves the
+// re-read inputs, which costs more than the exposed checkpoint loads.
 #pragma once
 
 #include "mtg_twisted_tmem_v4_kernel.cuh"
@@ -37,12 +42,11 @@ template <int N, int D>
 __host__ __device__ constexpr int chunked_ckpt_slots() {
   return (N / 2 - 1) * (N / 2 - 1) + (N / 2 - 1) * D;
 }
-// dynamic shared memory: [holder][staging][ring RD x (1+D)][times C+1][stash D+1][restart 1+2D][checkpoint][smem blocks]
+// dynamic shared memory: [holder][staging][ring RD x (1+D)][times C+1][stash D+1][restart 1+2D][smem blocks]
 template <int N, int D, int RD>
 __host__ __device__ constexpr size_t chunked_smem_bytes(int C, int ntm) {
   return size_t(kTmemHeaderBytes) + size_t(kTmemThreads / 32) * tmem_stage_bytes_per_warp<N, D>() +
-         size_t(RD * (1 + D) + (C + 1) + (D + 1) + (1 + 2 * D) + chunked_ckpt_slots<N, D>() +
-                (C - ntm) * v4_state_slots<N, D>()) * kTmemThreads * 8;
+         size_t(RD * (1 + D) + (C + 1) + (D + 1) + (1 + 2 * D) + (C - ntm) * v4_state_slots<N, D>()) * kTmemThreads * 8;
 }
 
 template <int N, int R, int D, int RD>
@@ -82,8 +86,7 @@ __global__ void __launch_bounds__(kTmemThreads, 2)
   auto HT = [&](int b) -> double& { return thist[size_t(b) * kTmemThreads]; };  // time of the step that made block b
   double* stash = thist + size_t(C + 1) * kTmemThreads;    // x0[D], T0
   double* restart = stash + size_t(D + 1) * kTmemThreads;  // T of own segment lo, x_lo[D], x_{lo+1}[D]
-  double* cks = restart + size_t(1 + 2 * D) * kTmemThreads;  // next round's checkpoint (W, y), prefetched
-  double* spill = cks + size_t(kCk) * kTmemThreads;
+  double* spill = restart + size_t(1 + 2 * D) * kTmemThreads;
   auto SP = [&](int blk, int slot) -> double& { return spill[(size_t(blk) * kSlots + slot) * kTmemThreads]; };
   auto RS = [&](int slot) -> double* { return restart + size_t(slot) * kTmemThreads; };
 
@@ -242,29 +245,24 @@ __global__ void __launch_bounds__(kTmemThreads, 2)
       const int lo = hi - C > 0 ? hi - C : 0;
       const int from = j == 0 ? 0 : lo;  // round 0 sweeps everything, storing only (lo, hi]
 
-      // ---- (re)start state: inputs through the restart slots, carry from the prologue (round 0) or checkpoint.
-      // Round 0 issues its loads here (once per tile); every later round finds restart inputs, checkpoint and the
-      // first ring entries already in shared memory: they were requested at the start of the previous round's
-      // back-substitution (round_prefetch below), a whole sweep earlier.
-      if (j == 0) {
-        restart_issue(from);
-        cp_async_commit();
+      // ---- (re)start state: inputs through the restart slots, carry from the prologue (round 0) or checkpoint
+      restart_issue(from);
+      cp_async_commit();
 #pragma unroll
-        for (int q = 1; q < RD; ++q) {
-          if (from + q <= nh && from + q <= hi) ring_issue(from + q);
-          cp_async_commit();
-        }
-        cp_async_wait_group<RD - 1>();
-      } else {
-        cp_async_wait_group<0>();
+      for (int q = 1; q < RD; ++q) {
+        if (from + q <= nh && from + q <= hi) ring_issue(from + q);
+        cp_async_commit();
+      }
+      if (j > 0) {
 #pragma unroll
         for (int a = 0; a < m; ++a) {
 #pragma unroll
-          for (int b = 0; b < m; ++b) Wp[a][b] = cks[size_t(a * m + b) * kTmemThreads];
+          for (int b = 0; b < m; ++b) Wp[a][b] = CK(j, a * m + b);
 #pragma unroll
-          for (int d = 0; d < D; ++d) yp[a][d] = cks[size_t(m * m + a * D + d) * kTmemThreads];
+          for (int d = 0; d < D; ++d) yp[a][d] = CK(j, m * m + a * D + d);
         }
       }
+      cp_async_wait_group<RD - 1>();
       {
         const double Tp = *RS(0);
 #pragma unroll
@@ -512,20 +510,6 @@ __global__ void __launch_bounds__(kTmemThreads, 2)
           for (int jj = 0; jj < m; ++jj) ed[1 + jj][d] = um[jj][d];
         }
         if (half == 0) store_free(nh + 1, ed);
-      }
-
-      // ---- next round's restart inputs, checkpoint and first ring entries: requested now, consumed after this
-      // round's back-substitution (ring, restart and checkpoint slots are idle during it)
-      if (j + 1 < nc) {
-        const int hi_n = n - (j + 1) * C;
-        const int lo_n = hi_n - C > 0 ? hi_n - C : 0;
-        restart_issue(lo_n);
-#pragma unroll
-        for (int q = 0; q < kCk; ++q) cp_async8(cks + size_t(q) * kTmemThreads, &CK(j + 1, q));
-#pragma unroll
-        for (int q = 1; q < RD; ++q)
-          if (lo_n + q <= nh && lo_n + q <= hi_n) ring_issue(lo_n + q);
-        cp_async_commit();
       }
 
       // ---- back-substitution + emission over (lo, hi], outwards

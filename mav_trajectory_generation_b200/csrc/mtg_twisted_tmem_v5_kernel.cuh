@@ -1,0 +1,585 @@
+// mtg_twisted_tmem_v5_kernel.cuh -- K1 (v5): the persistent twisted TMEM kernel with its INPUTS MOVED BY THE TMA.
+//
+// For short trajectories (K <= 8) the whole input record of a 16-trajectory warp tile -- seg_times[16][K] and
+// d_fixed[16][D][n_fixed], two contiguous spans of global memory -- fits in shared memory twice next to the
+// coefficient staging tile.  One elected lane fetches the NEXT tile with two cp.async.bulk copies completing on an
+// mbarrier while the warp works on the current tile (a full tile of lead), and every lane then reads its segment
+// times, waypoints and end derivatives from shared memory.  Compared with v4 this removes every per-lane global
+// load (LDG / LDGSTS: 16 distinct 128-byte lines per warp instruction), the cp.async ring, the time history, the
+// prologue prefetch region and their address arithmetic; what is left on the LSU are shared-memory accesses and
+// the TMA descriptors.  Requirements (checked by the host, which otherwise launches v4): B a multiple of 16 and
+// 16-byte aligned seg_times / d_fixed, so that every tile is a whole, aligned bulk copy.
+// Arithmetic per trajectory is the v3/v4 sequence: results are bitwise identical.
+#pragma once
+
+#include "mtg_twisted_tmem_v4_kernel.cuh"
+
+namespace mtg {
+
+struct TmemLaunchV5 {
+  int n_tmem_blocks;
+  int tmem_cols;
+  unsigned long long* tile_counter;  // non-null: dynamic tile assignment
+};
+
+// dynamic shared memory: [holder 128][staging x 4 warps][mbarriers 128][input tiles: 4 warps x 2 x 16*(K + D*nf)][spill]
+template <int N, int D>
+__host__ __device__ constexpr size_t v5_smem_bytes(int K, int nf, int ntm) {
+  const int nmax = (K + 1) / 2 - 1;
+  const int spill = (nmax - ntm) > 0 ? (nmax - ntm) * v4_state_slots<N, D>() : 0;
+  return size_t(kTmemHeaderBytes) + size_t(kTmemThreads / 32) * tmem_stage_bytes_per_warp<N, D>() + 128 +
+         size_t(kTmemThreads / 32) * 2 * 16 * size_t(K + D * nf) * 8 + size_t(spill) * kTmemThreads * 8;
+}
+
+namespace bulk {
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (bytes a multiple of 16, both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+}  // namespace bulk
+
+template <int N, int R, int D, int MINB>
+__global__ void __launch_bounds__(kTmemThreads, MINB)
+    twisted_tmem_v5_kernel(const WaypointParams prm, const TmemLaunchV5 tl, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int h = N / 2;
+  constexpr int m = h - 1;
+  constexpr int kL = m * (m + 1) / 2;
+  constexpr int kSlots = kL + m * D + D;
+  constexpr int kWords = 2 * kSlots;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int kWarps = kTmemThreads / 32;
+  constexpr double kTiny = 0x1p-600, kHuge = 0x1p+600;
+  using G = H1Imm<N, R>;
+  using AI = A1InvImm<N>;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int half = lane & 1;
+  const int K = prm.K;
+  const int nf = prm.n_fixed;
+  const int M = (K + 1) >> 1;
+  const int nh = half ? K - M - 1 : M - 1;
+  const int nmax = M - 1;
+  const int ntm = tl.n_tmem_blocks;
+
+  uint32_t* holder = reinterpret_cast<uint32_t*>(smem_raw);
+  double2* stage = reinterpret_cast<double2*>(smem_raw + kTmemHeaderBytes) + size_t(warp) * 32 * (D * h);
+  unsigned char* after_stage = smem_raw + kTmemHeaderBytes + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>();
+  const uint32_t bar0 = tmem::smem_u32(after_stage) + uint32_t(warp) * 16;  // two 8-byte mbarriers per warp
+  const int tile_t = 16 * K, tile_f = 16 * D * nf, tile_doubles = tile_t + tile_f;
+  double* tiles = reinterpret_cast<double*>(after_stage + 128) + size_t(warp) * 2 * tile_doubles;
+  double* spill = reinterpret_cast<double*>(after_stage + 128) + size_t(kWarps) * 2 * tile_doubles + threadIdx.x;
+  auto SP = [&](int blk, int slot) -> double& { return spill[(size_t(blk) * kSlots + slot) * kTmemThreads]; };
+
+  uint32_t tbase = 0;
+  if (tl.tmem_cols > 0) {
+    if (warp == 0) tmem::alloc(tmem::smem_u32(holder), (uint32_t)tl.tmem_cols);
+    tmem::fence_before_sync();
+    __syncthreads();
+    tmem::fence_after_sync();
+    tbase = *holder + (uint32_t(warp * 32) << 16);
+  }
+  auto put_state = [&](int blk, const double (&sv)[kSlots]) {
+    if (blk < ntm) {
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) {
+        const uint32_t w[2] = {(uint32_t)__double2loint(sv[i]), (uint32_t)__double2hiint(sv[i])};
+        tmem::st<2>(tbase + uint32_t(blk * kWords + 2 * i), w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) SP(blk - ntm, i) = sv[i];
+    }
+  };
+  // The tensor-memory read is asynchronous until tcgen05.wait::ld: state_issue() starts it, the caller does the
+  // work that does not depend on the state (segment time, its powers, E_v u_{v+1}), state_finish() waits.
+  auto state_issue = [&](int blk, uint32_t (&w)[kWords]) {
+    if (blk < ntm) tmem::ld_words<kWords>(tbase + uint32_t(blk * kWords), w);
+  };
+  auto state_finish = [&](int blk, const uint32_t (&w)[kWords], double (&sv)[kSlots]) {
+    if (blk < ntm) {
+      tmem::wait_ld();
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) sv[i] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) sv[i] = SP(blk - ntm, i);
+    }
+  };
+
+
+  auto seg = [&](int j) -> int { return half ? K - 1 - j : j; };
+  auto pidx = [&](int v) -> int {
+    const int o = half ? K - v : v;
+    return o == 0 ? 0 : (o < K ? h + o - 1 : h + K - 1);
+  };
+  auto sgn = [&](int idx) -> double { return (half && !(idx & 1)) ? -1.0 : 1.0; };
+  const int e0 = half ? h + K : 1;
+
+  const long long n_wtiles = prm.B >> 4;  // B is a multiple of 16 (host-checked)
+  const long long wt_stride = (long long)gridDim.x * kWarps;
+  const bool dyn = tl.tile_counter != nullptr;
+  auto draw_tile = [&]() -> long long { return lane == 0 ? (long long)atomicAdd(tl.tile_counter, 1ULL) : 0; };
+  // dynamic assignment draws TWO tiles ahead so that the atomic's round trip never sits in front of a fetch
+  long long wt = dyn ? __shfl_sync(kFull, draw_tile(), 0) : (long long)blockIdx.x * kWarps + warp;
+  long long pending = dyn ? draw_tile() : 0;  // lane 0 holds the tile after `wt`
+
+  // one elected lane moves a whole tile: seg_times[16][K] and d_fixed[16][D][nf] are contiguous in global memory
+  if (lane == 0) {
+    bulk::mbar_init(bar0, 1);
+    bulk::mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto fetch_tile = [&](long long w, int buf) {
+    if (lane == 0) {
+      const uint32_t bar = bar0 + 8u * buf;
+      double* dst = tiles + size_t(buf) * tile_doubles;
+      bulk::mbar_expect_tx(bar, uint32_t(tile_doubles) * 8u);
+      bulk::copy_g2s(tmem::smem_u32(dst), prm.times + w * 16 * K, uint32_t(tile_t) * 8u, bar);
+      bulk::copy_g2s(tmem::smem_u32(dst + tile_t), prm.dfix + w * 16 * (long long)D * nf, uint32_t(tile_f) * 8u, bar);
+    }
+  };
+  if (wt < n_wtiles) fetch_tile(wt, 0);
+
+  double2* my_row = stage + ((lane & 1) * 16 + (lane >> 1)) * (D * h);
+  const int nhF = M - 1, nhB = K - M - 1;
+  const int tl_row = lane >> 1;  // this lane's trajectory inside the tile
+
+  for (int it = 0; wt < n_wtiles; ++it) {
+    const int buf = it & 1;
+    // draw the next tile now and fetch it into the other buffer: a whole tile of lead.  The other buffer was read
+    // (generic proxy) by the previous tile; order those reads before the asynchronous-proxy write.
+    long long wt_next = dyn ? __shfl_sync(kFull, pending, 0) : wt + wt_stride;
+    if (dyn) pending = draw_tile();
+    fence_proxy_async();
+    __syncwarp();
+    if (wt_next < n_wtiles) fetch_tile(wt_next, buf ^ 1);
+    bulk::mbar_wait(bar0 + 8u * buf, uint32_t(it >> 1) & 1u);
+
+    const double* __restrict__ tT = tiles + size_t(buf) * tile_doubles + tl_row * K;
+    const double* __restrict__ tF = tiles + size_t(buf) * tile_doubles + tile_t + tl_row * (D * nf);
+    auto in_T = [&](int j) -> double { return tT[seg(j)]; };
+    auto in_x = [&](int v, int d) -> double { return tF[d * nf + pidx(v)]; };
+    const long long traj0 = wt * 16;
+    const long long traj = traj0 + tl_row;
+
+    // emit own-frame segment j for every lane of the warp at once (convergent)
+    auto emit_all = [&](int j, int v_step, double T, double iT, const double (&sd)[h][D], const double (&ed)[h][D]) {
+      double tp[h], itp[h];
+      const double Ts = half ? -T : T;
+      tp[0] = 1.0;
+#pragma unroll
+      for (int k = 1; k < h; ++k) tp[k] = tp[k - 1] * Ts;
+      itp[0] = pow_int<h>(iT);
+#pragma unroll
+      for (int k = 1; k < h; ++k) itp[k] = itp[k - 1] * iT;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        double c[N], ss[h], se[h];
+#pragma unroll
+        for (int k = 0; k < h; ++k) {
+          const double s0 = half ? ed[k][d] : sd[k][d];
+          const double e0v = half ? sd[k][d] : ed[k][d];
+          c[k] = s0 * ((half && (k & 1)) ? -AI::at(k, k) : AI::at(k, k));
+          ss[k] = tp[k] * s0;
+          se[k] = tp[k] * e0v;
+        }
+        double ee[h];
+#pragma unroll
+        for (int k = 0; k < h; ++k) {
+          double acc = se[k] - ss[k];
+#pragma unroll
+          for (int j2 = k + 1; j2 < h; ++j2) {
+            constexpr double kInvFact[6] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0};
+            acc = (j2 - k == 1) ? acc - ss[j2] : fma(-kInvFact[j2 - k], ss[j2], acc);
+          }
+          ee[k] = acc;
+        }
+#pragma unroll
+        for (int q = 0; q < h; ++q) {
+          double acc = AI::at(h + q, h) * ee[0];
+#pragma unroll
+          for (int k = 1; k < h; ++k) acc = fma(AI::at(h + q, h + k), ee[k], acc);
+          c[h + q] = acc * itp[q];
+        }
+        if (d == 0) {  // the TMA must have finished reading the previous segment's tile
+          if (lane == 0) bulk_wait_read();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < h; ++q) my_row[d * h + q] = make_double2(c[2 * q], c[2 * q + 1]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (v_step <= nhF) tma_store_box(&tmap, stage, j * (D * N), (int)traj0);
+        if (v_step <= nhB) tma_store_box(&tmap, stage + 16 * (D * h), (K - 1 - j) * (D * N), (int)traj0);
+        bulk_commit();
+      }
+    };
+
+
+    int stat = 0;
+    double Wp[m][m], yp[m][D], Cee[m][m], cps[m], cpe[m], xm[D], xc[D];
+    {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        xm[d] = in_x(0, d);
+        xc[d] = in_x(1, d);
+      }
+      const double T0 = in_T(0);
+      if (!(T0 > 0.0)) stat |= kStatusBadTime;
+      const double iT0 = fast_rcp(T0);
+      double pw[N - 1];
+      segment_powers<N, R>(T0, iT0, pw);
+#pragma unroll
+      for (int a = 0; a < m; ++a) {
+#pragma unroll
+        for (int b = 0; b < m; ++b) {
+          Cee[a][b] = pw[a + b + 2] * G::at(h + 1 + a, h + 1 + b);
+          Wp[a][b] = (a == b) ? kTiny : 0.0;
+        }
+        cps[a] = pw[a + 1] * G::at(h + 1 + a, 0);
+        cpe[a] = pw[a + 1] * G::at(h + 1 + a, h);
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        double u0[m];
+#pragma unroll
+        for (int b = 0; b < m; ++b) u0[b] = sgn(b) * tF[d * nf + e0 + b];
+#pragma unroll
+        for (int a = 0; a < m; ++a) {
+          double acc = 0.0;
+#pragma unroll
+          for (int b = 0; b < m; ++b) acc = fma(pw[a + b + 2] * G::at(h + 1 + a, 1 + b), u0[b], acc);
+          yp[a][d] = acc * kHuge;
+        }
+      }
+    }
+
+    // ---------------------------------------------------------------- sweep towards the middle
+    for (int v = 1; v <= nmax; ++v) {
+      double sv[kSlots];
+      if (v <= nh) {
+        double xn[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xn[d] = in_x(v + 1, d);
+        const double T = in_T(v);
+        if (!(T > 0.0)) stat |= kStatusBadTime;
+        const double iT = fast_rcp(T);
+        double pw[N - 1];
+        segment_powers<N, R>(T, iT, pw);
+
+        double Dp[m][m], E[m][m], bb[m][D];
+#pragma unroll
+        for (int a = 0; a < m; ++a) {
+#pragma unroll
+          for (int b = 0; b <= a; ++b) {
+            double s = fma(pw[a + b + 2], G::at(1 + a, 1 + b), Cee[a][b]);
+#pragma unroll
+            for (int k = 0; k < m; ++k) s = fma(-Wp[k][a], Wp[k][b], s);
+            Dp[a][b] = s;
+          }
+#pragma unroll
+          for (int b = 0; b < m; ++b) E[a][b] = pw[a + b + 2] * G::at(1 + a, h + 1 + b);
+          const double gmid = fma(pw[a + 1], G::at(1 + a, 0), cpe[a]);
+          const double gnext = pw[a + 1] * G::at(1 + a, h);
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            double s = -cps[a] * xm[d];
+            s = fma(-gmid, xc[d], s);
+            s = fma(-gnext, xn[d], s);
+#pragma unroll
+            for (int k = 0; k < m; ++k) s = fma(-Wp[k][a], yp[k][d], s);
+            bb[a][d] = s;
+          }
+        }
+        double L[m][m], inv[m];
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+          double s = Dp[j][j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
+          if (!(s > 0.0)) stat |= kStatusNotSpd;
+          inv[j] = fast_rsqrt(s);
+#pragma unroll
+          for (int i = j + 1; i < m; ++i) {
+            double t = Dp[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fma(-L[i][k], L[j][k], t);
+            L[i][j] = t * inv[j];
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+#pragma unroll
+          for (int j = 0; j < m; ++j) {
+            double s = bb[j][d];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s = fma(-L[j][k], yp[k][d], s);
+            yp[j][d] = s * inv[j];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < m; ++c) {
+#pragma unroll
+          for (int j = 0; j < m; ++j) {
+            double s = E[j][c];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s = fma(-L[j][k], Wp[k][c], s);
+            Wp[j][c] = s * inv[j];
+          }
+        }
+        {
+          int slot = 0;
+#pragma unroll
+          for (int i = 1; i < m; ++i)
+#pragma unroll
+            for (int j = 0; j < i; ++j) sv[slot++] = L[i][j];
+#pragma unroll
+          for (int j = 0; j < m; ++j) sv[slot++] = inv[j];
+#pragma unroll
+          for (int j = 0; j < m; ++j)
+#pragma unroll
+            for (int d = 0; d < D; ++d) sv[slot++] = yp[j][d];
+#pragma unroll
+          for (int d = 0; d < D; ++d) sv[slot++] = xc[d];
+        }
+#pragma unroll
+        for (int a = 0; a < m; ++a) {
+#pragma unroll
+          for (int b = 0; b <= a; ++b) Cee[a][b] = pw[a + b + 2] * G::at(h + 1 + a, h + 1 + b);
+          cps[a] = pw[a + 1] * G::at(h + 1 + a, 0);
+          cpe[a] = pw[a + 1] * G::at(h + 1 + a, h);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          xm[d] = xc[d];
+          xc[d] = xn[d];
+        }
+      }
+      __syncwarp();
+      put_state(v - 1, sv);
+    }
+    __syncwarp();
+    if (ntm > 0) tmem::wait_st();
+
+    // ---------------------------------------------------------------- middle vertex
+    double um[m][D];
+    {
+      double Dl[m][m], bl[m][D];
+#pragma unroll
+      for (int a = 0; a < m; ++a) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          double s = Cee[a][b];
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = fma(-Wp[k][a], Wp[k][b], s);
+          Dl[a][b] = s;
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          double s = -cps[a] * xm[d];
+          s = fma(-cpe[a], xc[d], s);
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = fma(-Wp[k][a], yp[k][d], s);
+          bl[a][d] = s;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < m; ++a) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          const double o = __shfl_xor_sync(kFull, Dl[a][b], 1);
+          Dl[a][b] += ((a + b) & 1) ? -o : o;
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const double o = __shfl_xor_sync(kFull, bl[a][d], 1);
+          bl[a][d] += (a & 1) ? o : -o;
+        }
+      }
+      stat |= __shfl_xor_sync(kFull, stat, 1);
+      double L[m][m], inv[m];
+#pragma unroll
+      for (int j = 0; j < m; ++j) {
+        double s = Dl[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
+        if (!(s > 0.0)) stat |= kStatusNotSpd;
+        inv[j] = fast_rsqrt(s);
+#pragma unroll
+        for (int i = j + 1; i < m; ++i) {
+          double t = Dl[i][j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) t = fma(-L[i][k], L[j][k], t);
+          L[i][j] = t * inv[j];
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        double y[m];
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+          double s = bl[j][d];
+#pragma unroll
+          for (int k = 0; k < j; ++k) s = fma(-L[j][k], y[k], s);
+          y[j] = s * inv[j];
+        }
+#pragma unroll
+        for (int j = m - 1; j >= 0; --j) {
+          double s = y[j];
+#pragma unroll
+          for (int k = j + 1; k < m; ++k) s = fma(-L[k][j], um[k][d], s);
+          um[j][d] = s * inv[j];
+        }
+      }
+    }
+    if (half == 0 && prm.status != nullptr) prm.status[traj] = stat;
+
+    // ---------------------------------------------------------------- outward back-substitution
+    const int np = (K - 1) * m;
+    double* __restrict__ df = prm.dfree != nullptr ? prm.dfree + traj * (long long)D * np : nullptr;
+    auto store_free = [&](int v_own, const double (&u)[h][D]) {
+      if (df != nullptr) {
+        const int vo = half ? K - v_own : v_own;
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+          for (int j = 0; j < m; ++j) df[d * np + (vo - 1) * m + j] = sgn(j) * u[1 + j][d];
+      }
+    };
+
+    double ed[h][D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      ed[0][d] = xc[d];
+#pragma unroll
+      for (int j = 0; j < m; ++j) ed[1 + j][d] = um[j][d];
+    }
+    if (half == 0) store_free(nh + 1, ed);
+
+    for (int v = nmax; v >= 1; --v) {
+      double sv[kSlots];
+      {
+        uint32_t w[kWords];
+        state_issue(v - 1, w);
+        state_finish(v - 1, w, sv);
+      }
+      const bool act = v <= nh;
+      double T = 1.0, iT = 1.0;
+      double sd[h][D];
+      if (act) {
+        double xv[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xv[d] = sv[kL + m * D + d];
+        T = in_T(v);
+        iT = fast_rcp(T);
+        double pw[N - 1];
+        segment_powers<N, R>(T, iT, pw);
+        double tE[m][D];
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+          for (int a = 0; a < m; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < m; ++b) s = fma(pw[a + b + 2] * G::at(1 + a, h + 1 + b), ed[1 + b][d], s);
+            tE[a][d] = s;
+          }
+        double L[m][m], inv[m], rhs[m][D];
+        {
+          int slot = 0;
+#pragma unroll
+          for (int i = 1; i < m; ++i)
+#pragma unroll
+            for (int j = 0; j < i; ++j) L[i][j] = sv[slot++];
+#pragma unroll
+          for (int j = 0; j < m; ++j) inv[j] = sv[slot++];
+#pragma unroll
+          for (int j = 0; j < m; ++j)
+#pragma unroll
+            for (int d = 0; d < D; ++d) rhs[j][d] = sv[slot++];
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          double t[m];
+#pragma unroll
+          for (int j = 0; j < m; ++j) {
+            double s = tE[j][d];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s = fma(-L[j][k], t[k], s);
+            t[j] = s * inv[j];
+            rhs[j][d] -= t[j];
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+#pragma unroll
+          for (int j = m - 1; j >= 0; --j) {
+            double s = rhs[j][d];
+#pragma unroll
+            for (int k = j + 1; k < m; ++k) s = fma(-L[k][j], sd[1 + k][d], s);
+            sd[1 + j][d] = s * inv[j];
+          }
+          sd[0][d] = xv[d];
+        }
+        store_free(v, sd);
+      }
+      __syncwarp();
+      emit_all(v, v, T, iT, sd, ed);
+      if (act) {
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+          for (int k = 0; k < h; ++k) ed[k][d] = sd[k][d];
+      }
+    }
+    {
+      double sd[h][D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        sd[0][d] = in_x(0, d);
+#pragma unroll
+        for (int b = 0; b < m; ++b) sd[1 + b][d] = sgn(b) * tF[d * nf + e0 + b];
+      }
+      const double T = in_T(0);
+      const double iT = fast_rcp(T);
+      __syncwarp();
+      emit_all(0, 0, T, iT, sd, ed);
+    }
+    wt = wt_next;
+  }
+
+  if (lane == 0) bulk_wait_all();
+  if (tl.tmem_cols > 0) {
+    tmem::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem::dealloc(*holder, (uint32_t)tl.tmem_cols);
+  }
+}
+
+}  // namespace mtg

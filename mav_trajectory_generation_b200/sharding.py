@@ -109,6 +109,56 @@ def solve_scattered(solve_fn, times_root, dfix_root, total, K, D, N, n_fixed, de
                                 chunks=chunks)
 
 
+# ---- fused solve + gather over NVLink peer memory (no collective, no intermediate buffers) --------------------------
+#
+# The B200-first form of "gather the solved coefficients": every rank maps the ROOT's output tensor into its own
+# address space (CUDA IPC) and hands the solver a slice of it as the coefficient buffer -- the kernels' TMA tensor
+# stores then travel over NVLink / NVSwitch straight into their final place in the root's HBM while the sweep of
+# the following tiles continues.  The transfer overlaps the math tile by tile inside ONE kernel; there is no gather
+# step, no staging copy and no NCCL call on the data path (torch.distributed only carries the 64-byte IPC handle
+# once, and the barrier).  Inputs go the other way with one DMA per rank (peer copy of its contiguous slice).
+
+def share_from_root(tensor, root=0):
+    """Collective: returns, on every rank, a tensor aliasing `tensor` of rank `root` (the root gets its own tensor
+    back).  The root's tensor must stay alive for as long as the aliases are used."""
+    from torch.multiprocessing.reductions import reduce_tensor
+    rank = dist.get_rank()
+    payload = [reduce_tensor(tensor) if rank == root else None]
+    dist.broadcast_object_list(payload, src=root)
+    if rank == root:
+        return tensor
+    fn, args = payload[0]
+    alias = fn(*args)
+    # make sure this process has peer access from its compute device to the root's device enabled (torch enables it
+    # lazily on the first cross-device copy)
+    probe = torch.empty(1, dtype=alias.dtype, device=torch.device("cuda", torch.cuda.current_device()))
+    probe.copy_(alias.reshape(-1)[:1])
+    torch.cuda.synchronize()
+    return alias
+
+
+def peer_solve_into_root(solve_fn, times_alias, dfix_alias, out_alias, total, device, root=0, local_buffers=None):
+    """One step of the fused path.  times_alias / dfix_alias / out_alias come from share_from_root (on the root they
+    are the root's own tensors).  Every rank copies its input slice with one peer DMA each, then solves straight
+    into its slice of the root's output.  The caller brackets steps with a barrier + synchronize."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    bounds = shard_bounds(total, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    if hi <= lo:
+        return
+    if rank == root:
+        solve_fn(times_alias[lo:hi], dfix_alias[lo:hi], out_alias[lo:hi])
+        return
+    buf = local_buffers if local_buffers is not None else {}
+    if buf.get("n") != hi - lo:
+        buf["t"] = torch.empty((hi - lo,) + tuple(times_alias.shape[1:]), dtype=torch.float64, device=device)
+        buf["f"] = torch.empty((hi - lo,) + tuple(dfix_alias.shape[1:]), dtype=torch.float64, device=device)
+        buf["n"] = hi - lo
+    buf["t"].copy_(times_alias[lo:hi], non_blocking=True)   # peer DMA, NVLink
+    buf["f"].copy_(dfix_alias[lo:hi], non_blocking=True)
+    solve_fn(buf["t"], buf["f"], out_alias[lo:hi])           # TMA stores land in the root's HBM
+
+
 # ---- host side: NUMA placement of a rank's pinned buffers ------------------------------------------------
 
 def gpu_numa_node(index):

@@ -88,7 +88,7 @@ def test_baseline_configs_8192_fixtures_vs_exact_and_oracle(solver, oracle, name
           f"oracle-exact max {e_oe.max():.2e}")
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])  # 1: thread per trajectory, 2: twisted, 3: + TMEM state, 4: persistent
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 6])  # 1: thread/trajectory, 2: twisted, 3: + TMEM state, 4: persistent, 6: + TMA inputs
 @pytest.mark.parametrize("N,r,K,D,B", [
     (10, 4, 16, 3, 4096),   # C3 headline shape, >= 4096 bit-exact fixture trajectories
     (10, 4, 8, 3, 2048),    # C2
@@ -173,6 +173,45 @@ def test_large_k_chunked_kernel(solver, oracle, K, B, chunk):
         dflt = solver.solve_linear(prob, t_d, f_d)
         torch.cuda.synchronize()
         assert torch.equal(dflt, out) or chunk != 0
+
+
+@pytest.mark.parametrize("N,r,K,D,B", [(10, 4, 8, 3, 65536), (10, 4, 2, 3, 4112), (10, 4, 7, 3, 16), (10, 4, 5, 3, 1600),
+                                       (8, 3, 4, 3, 131072), (8, 3, 8, 3, 48), (10, 4, 6, 1, 2048), (10, 3, 3, 3, 320)])
+def test_tma_input_kernel_bitwise_vs_resident(solver, oracle, N, r, K, D, B):
+    """K1v5 (inputs moved as whole tiles by cp.async.bulk + mbarrier, double buffered, persistent warps): bitwise
+    equal to the per-tile kernel on the same inputs -- many tiles per warp (buffer reuse, mbarrier phase flips),
+    a single tile, odd K, dynamic and static tile assignment; d_free and status outputs included."""
+    import torch
+    import mav_trajectory_generation_b200 as m
+    rng = np.random.RandomState(K * 100 + D)
+    pos = rng.uniform(-10, 10, size=(B, K + 1, D))
+    dist = np.maximum(np.linalg.norm(np.diff(pos, axis=1), axis=2), 0.2)
+    times = dist / 3.0 * 2 * (1.0 + 6.5 * 3.0 / 5.0 * np.exp(-dist / 3.0 * 2))
+    sd = rng.uniform(-1, 1, size=(B, N // 2 - 1, D))
+    ed = rng.uniform(-1, 1, size=(B, N // 2 - 1, D))
+    prob = m.Problem(N, r, K, D)
+    t_d = torch.from_numpy(np.ascontiguousarray(times)).cuda()
+    f_d = torch.from_numpy(oracle.waypoint_d_fixed(N, pos, sd, ed)).cuda()
+    outs = {}
+    for variant, dyn in ((3, 0), (6, 1), (6, 2)):
+        solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, variant)
+        solver.set_option(m.capi.OPT_DYNAMIC_TILES, dyn)
+        try:
+            st = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+            df = torch.zeros((B, D, max(prob.n_free, 1)), dtype=torch.float64, device="cuda")
+            out = solver.solve_linear(prob, t_d, f_d, status=st, d_free=df)
+            torch.cuda.synchronize()
+        finally:
+            solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, 0)
+            solver.set_option(m.capi.OPT_DYNAMIC_TILES, 0)
+        assert bool((st == 0).all())
+        outs[(variant, dyn)] = (out, df)
+    for key in ((6, 1), (6, 2)):
+        assert torch.equal(outs[key][0], outs[(3, 0)][0]), key
+        assert torch.equal(outs[key][1], outs[(3, 0)][1]), key
+    sub = slice(0, min(B, 256))
+    exact = oracle.exact_solve_batch(N, r, times[sub], oracle.waypoint_d_fixed(N, pos, sd, ed)[sub])
+    assert global_rel_err(outs[(6, 1)][0][sub].cpu().numpy(), exact).max() <= 1e-10
 
 
 @pytest.mark.parametrize("N,r,K,D,seed", [(10, 4, 16, 3, 1000), (10, 4, 16, 1, 1003), (10, 3, 5, 3, 110), (10, 2, 5, 3, 109),

@@ -17,11 +17,13 @@ def main():
     dev = torch.device("cuda:0")
     s = m.Solver(0)
     cfgs = [("C3", 10, 4, 16, 3, 262144), ("C2", 10, 4, 8, 3, 65536), ("C4", 8, 3, 4, 3, 1048576),
-            ("C5x1", 10, 4, 16, 3, 1048576), ("odd", 10, 4, 7, 3, 100001)]
+            ("K6", 10, 4, 6, 3, 262144), ("K2", 10, 4, 2, 3, 262144)]
     # (variant, ring depth, CTA cap [9 = one CTA per tile], stagger us, dynamic tiles)
     # ring depth "2" selects the ring-depth-3 kernel WITHOUT the hoisted outward-sweep work (A/B of the hoist)
-    variants = [(3, 0, 0, 0, 0), (4, 3, 0, 0, 1), (4, 3, 0, 0, 2), (0, 3, 0, 0, 0)]
+    variants = [(3, 0, 0, 0, 0), (4, 3, 0, 0, 1), (4, 3, 0, 0, 2), (6, 3, 0, 0, 1), (6, 3, 0, 0, 2)]
     rows = []
+    if "--large-only" in sys.argv:
+        cfgs = []
     for name, N, r, K, D, B in cfgs:
         prob = m.Problem(N, r, K, D)
         times, dfix = synth(N, K, D, B, dev)
