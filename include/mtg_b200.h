@@ -107,7 +107,7 @@ int mtg_device_is_sm100(const mtg_handle* h);
 #define MTG_OPT_CHUNK_BLOCKS 6    /* chunked (large-K) kernel: resident vertex blocks per lane, 0 = auto */
 #define MTG_OPT_GENERIC_VARIANT 7 /* arbitrary masks: 0 = masked block kernel (default), 1 = banded kernel in global scratch */
 #define MTG_OPT_MELLINGER_UNFUSED 8 /* 1 = batched Mellinger gradient through expand + solve + cost kernels */
-#define MTG_OPT_TMA_INPUTS 9      /* K <= 8: 1 = prefer the kernel that moves whole input tiles with TMA bulk copies */
+#define MTG_OPT_TMA_INPUTS 9      /* K <= 8: 1 (default) = prefer the kernel that moves whole input tiles with TMA bulk copies */
 #define MTG_OPT_DYNAMIC_TILES 5   /* persistent kernel: warps draw tiles from a global counter: 0 = auto, 1 = always, 2 = never */
 int mtg_set_option(mtg_handle* h, int key, int value);
 

@@ -52,7 +52,7 @@ struct mtg_handle {
   int ring_depth = 3;        // MTG_OPT_RING_DEPTH (v4 kernel: cp.async input ring buffers, 2..4)
   int ctas_per_sm = 0;       // MTG_OPT_CTAS_PER_SM (v4 kernel: 0 = as many as fit, 9 = one CTA per tile, not persistent)
   int stagger_us = 0;        // MTG_OPT_STAGGER_US (v4 kernel: CTA start times spread over this many microseconds)
-  int tma_inputs = 0;        // MTG_OPT_TMA_INPUTS (default routing prefers the TMA-input kernel v5 when eligible)
+  int tma_inputs = 1;        // MTG_OPT_TMA_INPUTS (default routing prefers the TMA-input kernel v5 when eligible)
   int mellinger_unfused = 0; // MTG_OPT_MELLINGER_UNFUSED (1 = expand + solve + cost kernels, the round-1 path)
   int generic_variant = 0;   // MTG_OPT_GENERIC_VARIANT (0 = masked block kernel, 1 = banded kernel in global scratch)
   int chunk_blocks = 0;      // MTG_OPT_CHUNK_BLOCKS (chunked kernel: resident vertex blocks per lane, 0 = auto)
@@ -244,7 +244,9 @@ struct V5Entry {
 const V5Entry kV5Kernels[] = {{10, 4, 3, mtg::twisted_tmem_v5_kernel<10, 4, 3, 2>},
                               {8, 3, 3, mtg::twisted_tmem_v5_kernel<8, 3, 3, 3>},
                               {10, 4, 1, mtg::twisted_tmem_v5_kernel<10, 4, 1, 2>},
-                              {10, 3, 3, mtg::twisted_tmem_v5_kernel<10, 3, 3, 2>}};
+                              {10, 3, 3, mtg::twisted_tmem_v5_kernel<10, 3, 3, 2>},
+                              {10, 2, 3, mtg::twisted_tmem_v5_kernel<10, 2, 3, 2>},
+                              {12, 5, 3, mtg::twisted_tmem_v5_kernel<12, 5, 3, 2>}};
 const V5Entry* find_v5(const mtg_problem* p) {
   for (const auto& e : kV5Kernels)
     if (e.N == p->N && e.R == p->r && e.D == p->D) return &e;

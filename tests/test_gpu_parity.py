@@ -179,8 +179,11 @@ def test_large_k_chunked_kernel(solver, oracle, K, B, chunk):
                                        (8, 3, 4, 3, 131072), (8, 3, 8, 3, 48), (10, 4, 6, 1, 2048), (10, 3, 3, 3, 320)])
 def test_tma_input_kernel_bitwise_vs_resident(solver, oracle, N, r, K, D, B):
     """K1v5 (inputs moved as whole tiles by cp.async.bulk + mbarrier, double buffered, persistent warps): bitwise
-    equal to the per-tile kernel on the same inputs -- many tiles per warp (buffer reuse, mbarrier phase flips),
-    a single tile, odd K, dynamic and static tile assignment; d_free and status outputs included."""
+    equal to the persistent kernel v4 on the same inputs (identical arithmetic, only the input path differs) --
+    many tiles per warp (buffer reuse, mbarrier phase flips), a single tile, odd K, dynamic and static tile
+    assignment, NON-ZERO end derivatives; d_free and status outputs included.  Against the per-tile kernel v3 the
+    results agree to rounding only: v4/v5 add the end-derivative carry of the first sweep step last instead of
+    first (the 2^+-600 folding)."""
     import torch
     import mav_trajectory_generation_b200 as m
     rng = np.random.RandomState(K * 100 + D)
@@ -193,7 +196,7 @@ def test_tma_input_kernel_bitwise_vs_resident(solver, oracle, N, r, K, D, B):
     t_d = torch.from_numpy(np.ascontiguousarray(times)).cuda()
     f_d = torch.from_numpy(oracle.waypoint_d_fixed(N, pos, sd, ed)).cuda()
     outs = {}
-    for variant, dyn in ((3, 0), (6, 1), (6, 2)):
+    for variant, dyn in ((3, 0), (4, 2), (6, 1), (6, 2)):
         solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, variant)
         solver.set_option(m.capi.OPT_DYNAMIC_TILES, dyn)
         try:
@@ -207,8 +210,10 @@ def test_tma_input_kernel_bitwise_vs_resident(solver, oracle, N, r, K, D, B):
         assert bool((st == 0).all())
         outs[(variant, dyn)] = (out, df)
     for key in ((6, 1), (6, 2)):
-        assert torch.equal(outs[key][0], outs[(3, 0)][0]), key
-        assert torch.equal(outs[key][1], outs[(3, 0)][1]), key
+        assert torch.equal(outs[key][0], outs[(4, 2)][0]), key
+        assert torch.equal(outs[key][1], outs[(4, 2)][1]), key
+    den = outs[(3, 0)][0].abs().reshape(B, -1).max(dim=1).values
+    assert float(((outs[(6, 1)][0] - outs[(3, 0)][0]).abs().reshape(B, -1).max(dim=1).values / den).max()) <= 1e-12
     sub = slice(0, min(B, 256))
     exact = oracle.exact_solve_batch(N, r, times[sub], oracle.waypoint_d_fixed(N, pos, sd, ed)[sub])
     assert global_rel_err(outs[(6, 1)][0][sub].cpu().numpy(), exact).max() <= 1e-10
