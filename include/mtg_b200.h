@@ -94,7 +94,8 @@ int64_t mtg_launch_count(const mtg_handle* h);
 int mtg_device_is_sm100(const mtg_handle* h);
 
 /* tuning knobs (results are identical to rounding; used by tests and profiles)
- *   MTG_OPT_WAYPOINT_VARIANT: 0 = default (4 for K <= 8, 3 up to the K whose factor fits on chip, 5 beyond),
+ *   MTG_OPT_WAYPOINT_VARIANT: 0 = default (6 where it applies, else 4 for K <= 8, 3 up to the K whose factor fits
+ *                                 on chip, 5 beyond),
  *                             1 = one thread per trajectory, 2 = twisted (state in shared memory),
  *                             3 = twisted with the sweep state in tensor memory + TMA tensor stores,
  *                             4 = persistent version of 3 with deep input prefetch,
@@ -107,7 +108,8 @@ int mtg_device_is_sm100(const mtg_handle* h);
 #define MTG_OPT_CHUNK_BLOCKS 6    /* chunked (large-K) kernel: resident vertex blocks per lane, 0 = auto */
 #define MTG_OPT_GENERIC_VARIANT 7 /* arbitrary masks: 0 = masked block kernel (default), 1 = banded kernel in global scratch */
 #define MTG_OPT_MELLINGER_UNFUSED 8 /* 1 = batched Mellinger gradient through expand + solve + cost kernels */
-#define MTG_OPT_TMA_INPUTS 9      /* K <= 8: 1 (default) = prefer the kernel that moves whole input tiles with TMA bulk copies */
+#define MTG_OPT_TMA_INPUTS 9      /* 0 = never, 1 = the TMA-input kernel (v5) where two input tiles fit (double buffered),
+                                    2 (default) = also where only one fits (single buffered) */
 #define MTG_OPT_DYNAMIC_TILES 5   /* persistent kernel: warps draw tiles from a global counter: 0 = auto, 1 = always, 2 = never */
 int mtg_set_option(mtg_handle* h, int key, int value);
 

@@ -52,7 +52,7 @@ struct mtg_handle {
   int ring_depth = 3;        // MTG_OPT_RING_DEPTH (v4 kernel: cp.async input ring buffers, 2..4)
   int ctas_per_sm = 0;       // MTG_OPT_CTAS_PER_SM (v4 kernel: 0 = as many as fit, 9 = one CTA per tile, not persistent)
   int stagger_us = 0;        // MTG_OPT_STAGGER_US (v4 kernel: CTA start times spread over this many microseconds)
-  int tma_inputs = 1;        // MTG_OPT_TMA_INPUTS (default routing prefers the TMA-input kernel v5 when eligible)
+  int tma_inputs = 2;        // MTG_OPT_TMA_INPUTS (default routing prefers the TMA-input kernel v5 when eligible)
   int mellinger_unfused = 0; // MTG_OPT_MELLINGER_UNFUSED (1 = expand + solve + cost kernels, the round-1 path)
   int generic_variant = 0;   // MTG_OPT_GENERIC_VARIANT (0 = masked block kernel, 1 = banded kernel in global scratch)
   int chunk_blocks = 0;      // MTG_OPT_CHUNK_BLOCKS (chunked kernel: resident vertex blocks per lane, 0 = auto)
@@ -85,6 +85,7 @@ struct mtg_handle {
   // cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION (shared by every K routed to it):
   // remember the largest value set so far and only ever raise it
   std::vector<std::pair<const void*, size_t>> smem_set;
+  std::vector<std::pair<const void*, int>> regs_of;  // cudaFuncGetAttributes().numRegs, queried once per function
   // last encoded tensor map (B = 1 solveLinear() calls re-use the same output buffer)
   struct TmapKey {
     const void* base = nullptr;
@@ -239,14 +240,12 @@ constexpr int kV4MaxK = 8;
 typedef void (*V5Kernel)(const mtg::WaypointParams, const mtg::TmemLaunchV5, const CUtensorMap);
 struct V5Entry {
   int N, R, D;
-  V5Kernel fn;
+  V5Kernel fn, fn_fused;
 };
-const V5Entry kV5Kernels[] = {{10, 4, 3, mtg::twisted_tmem_v5_kernel<10, 4, 3, 2>},
-                              {8, 3, 3, mtg::twisted_tmem_v5_kernel<8, 3, 3, 3>},
-                              {10, 4, 1, mtg::twisted_tmem_v5_kernel<10, 4, 1, 2>},
-                              {10, 3, 3, mtg::twisted_tmem_v5_kernel<10, 3, 3, 2>},
-                              {10, 2, 3, mtg::twisted_tmem_v5_kernel<10, 2, 3, 2>},
-                              {12, 5, 3, mtg::twisted_tmem_v5_kernel<12, 5, 3, 2>}};
+#define MTG_V5(N_, R_, D_, MB_) \
+  {N_, R_, D_, mtg::twisted_tmem_v5_kernel<N_, R_, D_, MB_, false>, mtg::twisted_tmem_v5_kernel<N_, R_, D_, MB_, true>}
+const V5Entry kV5Kernels[] = {MTG_V5(10, 4, 3, 2), MTG_V5(8, 3, 3, 3),  MTG_V5(10, 4, 1, 2),
+                              MTG_V5(10, 3, 3, 2), MTG_V5(10, 2, 3, 2), MTG_V5(12, 5, 3, 2)};
 const V5Entry* find_v5(const mtg_problem* p) {
   for (const auto& e : kV5Kernels)
     if (e.N == p->N && e.R == p->r && e.D == p->D) return &e;
@@ -340,6 +339,20 @@ int ensure_dyn_smem(mtg_handle* h, const void* fn, size_t bytes) {
   return MTG_OK;
 }
 
+// registers per thread of a kernel (cached: a B = 1 solveLinear() call must not pay an attribute query)
+int kernel_regs(mtg_handle* h, const void* fn, int* out) {
+  for (auto& kv : h->regs_of)
+    if (kv.first == fn) {
+      *out = kv.second;
+      return MTG_OK;
+    }
+  cudaFuncAttributes attr;
+  MTG_CUDA(h, cudaFuncGetAttributes(&attr, fn));
+  h->regs_of.emplace_back(fn, attr.numRegs);
+  *out = attr.numRegs;
+  return MTG_OK;
+}
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
@@ -398,9 +411,12 @@ int launch_chunked(mtg_handle* h, const mtg_problem* p, const WaypointEntry* e, 
   const int hh = p->N / 2, mm = hh - 1, D = p->D, rd = 3;
   const int kslots = mm * (mm + 1) / 2 + mm * D + D, kck = mm * mm + mm * D;
   const int nmax = (p->K + 1) / 2 - 1;
-  cudaFuncAttributes attr;
-  MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)e->fn_chunked));
-  const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
+  int n_regs = 0;
+  {
+    const int rc_regs = kernel_regs(h, (const void*)e->fn_chunked, &n_regs);
+    if (rc_regs != MTG_OK) return rc_regs;
+  }
+  const int by_regs = std::max(1, 65536 / (std::max(n_regs, 1) * mtg::kTmemThreads));
   auto smem_of = [&](int C, int ntm) {
     return size_t(mtg::kTmemHeaderBytes) + size_t(4) * e->stage_bytes_per_warp +
            size_t(rd * (1 + D) + (C + 1) + (D + 1) + (1 + 2 * D) + (C - ntm) * kslots) * mtg::kTmemThreads * 8;
@@ -544,9 +560,12 @@ int launch_cost_fused(mtg_handle* h, const mtg_problem* p, CachedTopology* topo,
   const WaypointEntry* e = L.waypoint ? find_waypoint(h, p, L) : nullptr;
   if (!ce || !e || L.n_free == 0) return MTG_ERR_ALLOC;
   const int nmax = (p->K + 1) / 2 - 1;
-  cudaFuncAttributes attr;
-  MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)ce->fn));
-  const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
+  int n_regs = 0;
+  {
+    const int rc_regs = kernel_regs(h, (const void*)ce->fn, &n_regs);
+    if (rc_regs != MTG_OK) return rc_regs;
+  }
+  const int by_regs = std::max(1, 65536 / (std::max(n_regs, 1) * mtg::kTmemThreads));
   int best_ctas = 0, best_cols = 0, best_ntm = 0;
   size_t best_smem = 0;
   const int col_options[] = {512, 256, 128, 64, 32, 0};
@@ -640,50 +659,65 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
     const bool coeffs_aligned = (reinterpret_cast<uintptr_t>(coeffs) & 15u) == 0;
     if (h->waypoint_variant == 5 && coeffs_aligned && !fused)
       return launch_chunked(h, p, e, prm, coeffs, B, stream, slot);
-    const bool v5_eligible = !fused && coeffs_aligned && p->K <= kV4MaxK && (B % 16) == 0 &&
-                             ((reinterpret_cast<uintptr_t>(times) | reinterpret_cast<uintptr_t>(dfix)) & 15u) == 0;
+    const bool v5_eligible =
+        coeffs_aligned && (B % 16) == 0 &&
+        (fused ? (reinterpret_cast<uintptr_t>(fused->positions) & 15u) == 0
+               : ((reinterpret_cast<uintptr_t>(times) | reinterpret_cast<uintptr_t>(dfix)) & 15u) == 0);
     if ((h->waypoint_variant == 6 || (h->waypoint_variant == 0 && h->tma_inputs)) && v5_eligible) {
       const V5Entry* e5 = find_v5(p);
       if (e5) {
+        const V5Kernel fn5 = fused ? e5->fn_fused : e5->fn;
         const int hh = p->N / 2, mm = hh - 1;
-        const int kslots = mm * (mm + 1) / 2 + mm * p->D + p->D;
+        const int kslots = mm * (mm + 1) / 2 + mm * p->D;  // no positions in the v5 state
         const int nmax = (p->K + 1) / 2 - 1;
-        cudaFuncAttributes attr;
-        MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)e5->fn));
-        const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
-        int best_ctas = 0, best_cols = 0, best_ntm = 0;
+        const int total_state = nmax * kslots;
+        int n_regs = 0;
+        {
+          const int rc_regs = kernel_regs(h, (const void*)fn5, &n_regs);
+          if (rc_regs != MTG_OK) return rc_regs;
+        }
+        const int by_regs = std::max(1, 65536 / (std::max(n_regs, 1) * mtg::kTmemThreads));
+        int best_ctas = 0, best_cols = 0, best_nbuf = 0;
         size_t best_smem = 0;
         const int col_options[] = {256, 128, 64, 32, 512};
-        for (int cols : col_options) {
-          const int ntm = std::min(nmax, cols / (2 * kslots));
-          if (ntm == 0 && nmax > 0) continue;
-          const int spill = std::max(0, nmax - ntm) * kslots;
-          const size_t smem = mtg::kTmemHeaderBytes + size_t(4) * e->stage_bytes_per_warp + 128 +
-                              size_t(4) * 2 * 16 * size_t(p->K + p->D * L.n_fixed) * 8 + size_t(spill) * mtg::kTmemThreads * 8;
-          if (smem > h->smem_optin) continue;
-          int ctas = std::min<int>(by_regs, int((228 * 1024) / (smem + 1024)));
-          ctas = std::min(std::min(ctas, 512 / cols), 8);
-          if (ctas > best_ctas || (ctas == best_ctas && smem < best_smem)) {
-            best_ctas = ctas;
-            best_cols = cols;
-            best_ntm = ntm;
-            best_smem = smem;
+        for (int nbuf = 2; nbuf >= 1; --nbuf)
+          for (int cols : col_options) {
+            const int tslots = cols / 2;
+            const int spill = std::max(0, total_state - tslots);
+            const size_t tile_doubles = fused ? size_t(16) * (p->K + 1) * p->D : size_t(16) * (p->K + p->D * L.n_fixed);
+            const size_t smem = mtg::kTmemHeaderBytes + size_t(4) * e->stage_bytes_per_warp + 128 +
+                                size_t(4) * nbuf * tile_doubles * 8 +
+                                size_t(spill + (fused ? nmax + 1 : 0)) * mtg::kTmemThreads * 8;
+            if (smem > h->smem_optin) continue;
+            int ctas = std::min<int>(by_regs, int((228 * 1024) / (smem + 1024)));
+            ctas = std::min(std::min(ctas, 512 / cols), 8);
+            // more resident CTAs first; then double buffering; then less shared memory
+            if (ctas > best_ctas || (ctas == best_ctas && ctas > 0 && (nbuf > best_nbuf || (nbuf == best_nbuf && smem < best_smem)))) {
+              best_ctas = ctas;
+              best_cols = cols;
+              best_nbuf = nbuf;
+              best_smem = smem;
+            }
           }
-        }
-        if (best_ctas >= 2) {
+        const bool take = best_ctas >= 2 && (h->waypoint_variant == 6 || best_nbuf == 2 || h->tma_inputs == 2);
+        if (take) {
           mtg::TmemLaunchV5 tl;
-          tl.n_tmem_blocks = best_ntm;
+          tl.tmem_slots = best_cols / 2;
           tl.tmem_cols = best_cols;
+          tl.n_buffers = best_nbuf;
           tl.tile_counter = nullptr;
           const int64_t blocks = std::min<int64_t>((B + 63) / 64, int64_t(best_ctas) * h->sm_count);
+          // dynamic tile counter for long tiles with several tiles per warp (balances the tail: C3 0.618 vs 0.605,
+          // C5 on one GPU 0.655 vs 0.630); static round-robin for short trajectories, where the atomic's round trip is
+          // not small against a tile (C2 0.581 vs 0.529, C4 0.812 vs 0.797)  [profiles/r02_k1_variants.json]
           const int64_t tiles_per_warp = (B / 16) / std::max<int64_t>(1, blocks * 4);
-          if (h->dynamic_tiles == 1 || (h->dynamic_tiles == 0 && tiles_per_warp >= 16)) {
+          if (h->dynamic_tiles == 1 || (h->dynamic_tiles == 0 && tiles_per_warp >= 8 && p->K > kV4MaxK)) {
             if (!h->tile_counters) MTG_CUDA(h, cudaMalloc(&h->tile_counters, sizeof(unsigned long long) * 32 * (mtg_handle::kPipe + 1)));
             tl.tile_counter = h->tile_counters + 32 * slot;
             MTG_CUDA(h, cudaMemsetAsync(tl.tile_counter, 0, sizeof(unsigned long long), stream));
           }
           {
-            const int rc_smem = ensure_dyn_smem(h, (const void*)e5->fn, best_smem);
+            const int rc_smem = ensure_dyn_smem(h, (const void*)fn5, best_smem);
             if (rc_smem != MTG_OK) return rc_smem;
           }
           CUtensorMap tmap;
@@ -691,7 +725,7 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
             const int rc = encode_coeff_tmap(h, &tmap, coeffs, B, p);
             if (rc != MTG_OK) return rc;
           }
-          e5->fn<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl, tmap);
+          fn5<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl, tmap);
           MTG_CUDA(h, cudaGetLastError());
           h->launches++;
           return MTG_OK;
@@ -706,9 +740,12 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
         const int hh = p->N / 2, mm = hh - 1;
         const int kslots = mm * (mm + 1) / 2 + mm * p->D + p->D, kpro = 2 * p->D + mm * p->D + 1;
         const int nmax = (p->K + 1) / 2 - 1;
-        cudaFuncAttributes attr;
-        MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)fn));
-        const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
+        int n_regs = 0;
+        {
+          const int rc_regs = kernel_regs(h, (const void*)fn, &n_regs);
+          if (rc_regs != MTG_OK) return rc_regs;
+        }
+        const int by_regs = std::max(1, 65536 / (std::max(n_regs, 1) * mtg::kTmemThreads));
         int best_ctas = 0, best_cols = 0, best_ntm = 0;
         size_t best_smem = 0;
         const int col_options[] = {512, 256, 128, 64, 32, 0};
@@ -776,9 +813,12 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
       for (auto& pl : h->plans)
         if (pl.entry == (const void*)e && pl.K == p->K) plan = &pl;
       if (!plan) {
-        cudaFuncAttributes attr;
-        MTG_CUDA(h, cudaFuncGetAttributes(&attr, (const void*)e->fn_tmem));
-        const int by_regs = std::max(1, 65536 / (std::max(attr.numRegs, 1) * mtg::kTmemThreads));
+        int n_regs = 0;
+        {
+          const int rc_regs = kernel_regs(h, (const void*)e->fn_tmem, &n_regs);
+          if (rc_regs != MTG_OK) return rc_regs;
+        }
+        const int by_regs = std::max(1, 65536 / (std::max(n_regs, 1) * mtg::kTmemThreads));
         mtg_handle::TmemPlan np;
         np.entry = (const void*)e;
         np.K = p->K;
@@ -1002,7 +1042,7 @@ int mtg_set_option(mtg_handle* h, int key, int value) {
     h->chunk_blocks = value;
     return MTG_OK;
   }
-  if (key == MTG_OPT_TMA_INPUTS && (value == 0 || value == 1)) {
+  if (key == MTG_OPT_TMA_INPUTS && value >= 0 && value <= 2) {
     h->tma_inputs = value;
     return MTG_OK;
   }

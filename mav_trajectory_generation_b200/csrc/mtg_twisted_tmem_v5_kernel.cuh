@@ -1,10 +1,14 @@
 // mtg_twisted_tmem_v5_kernel.cuh -- K1 (v5): the persistent twisted TMEM kernel with its INPUTS MOVED BY THE TMA.
 //
-// For short trajectories (K <= 8) the whole input record of a 16-trajectory warp tile -- seg_times[16][K] and
-// d_fixed[16][D][n_fixed], two contiguous spans of global memory -- fits in shared memory twice next to the
-// coefficient staging tile.  One elected lane fetches the NEXT tile with two cp.async.bulk copies completing on an
-// mbarrier while the warp works on the current tile (a full tile of lead), and every lane then reads its segment
-// times, waypoints and end derivatives from shared memory.  Compared with v4 this removes every per-lane global
+// The whole input record of a 16-trajectory warp tile -- seg_times[16][K] and d_fixed[16][D][n_fixed], two
+// contiguous spans of global memory -- is brought into shared memory by one elected lane with two cp.async.bulk
+// copies completing on an mbarrier, and every lane then reads its segment times, waypoints and end derivatives
+// from shared memory.  For short trajectories (K <= 8) two tiles fit next to the coefficient staging tile and the
+// NEXT tile is fetched a whole tile ahead; for longer ones (K = 16: 11.6 KB per tile) one tile fits beside the part
+// of the sweep state that overflows tensor memory, and the refill is issued while the last segment of the current
+// tile is emitted.  The waypoints are no longer copied into the sweep state (the tile stays resident), which
+// shrinks the state to 22 doubles per vertex, and the state is split between TMEM and shared memory slot by slot
+// instead of block by block (K = 16: 128 of 154 doubles per lane in TMEM, 26 in shared memory).  Compared with v4 this removes every per-lane global
 // load (LDG / LDGSTS: 16 distinct 128-byte lines per warp instruction), the cp.async ring, the time history, the
 // prologue prefetch region and their address arithmetic; what is left on the LSU are shared-memory accesses and
 // the TMA descriptors.  Requirements (checked by the host, which otherwise launches v4): B a multiple of 16 and
@@ -17,18 +21,29 @@
 namespace mtg {
 
 struct TmemLaunchV5 {
-  int n_tmem_blocks;
+  int tmem_slots;   // sweep-state doubles per lane held in tensor memory (= tmem_cols / 2); the state is split at SLOT
+                    // granularity: state double number s (block * 22 + slot at N = 10, D = 3) lives in TMEM when
+                    // s < tmem_slots, in shared memory otherwise
   int tmem_cols;
+  int n_buffers;    // input tiles per warp: 2 = next tile fetched a whole tile ahead (K <= 8), 1 = fetched while the
+                    // last segment is emitted (the state of longer trajectories leaves room for one tile only)
   unsigned long long* tile_counter;  // non-null: dynamic tile assignment
 };
 
-// dynamic shared memory: [holder 128][staging x 4 warps][mbarriers 128][input tiles: 4 warps x 2 x 16*(K + D*nf)][spill]
+// sweep state per eliminated vertex: L (strictly lower) + inverse pivots + y  (positions come from the input tile)
 template <int N, int D>
-__host__ __device__ constexpr size_t v5_smem_bytes(int K, int nf, int ntm) {
+__host__ __device__ constexpr int v5_state_slots() {
+  constexpr int m = N / 2 - 1;
+  return m * (m + 1) / 2 + m * D;
+}
+// dynamic shared memory: [holder 128][staging x 4 warps][mbarriers 128][input tiles: 4 warps x nbuf x 16*(K + D*nf)][spill]
+template <int N, int D>
+__host__ __device__ constexpr size_t v5_smem_bytes(int K, int nf, int tmem_slots, int nbuf) {
   const int nmax = (K + 1) / 2 - 1;
-  const int spill = (nmax - ntm) > 0 ? (nmax - ntm) * v4_state_slots<N, D>() : 0;
+  const int total = nmax * v5_state_slots<N, D>();
+  const int spill = total > tmem_slots ? total - tmem_slots : 0;
   return size_t(kTmemHeaderBytes) + size_t(kTmemThreads / 32) * tmem_stage_bytes_per_warp<N, D>() + 128 +
-         size_t(kTmemThreads / 32) * 2 * 16 * size_t(K + D * nf) * 8 + size_t(spill) * kTmemThreads * 8;
+         size_t(kTmemThreads / 32) * nbuf * 16 * size_t(K + D * nf) * 8 + size_t(spill) * kTmemThreads * 8;
 }
 
 namespace bulk {
@@ -59,13 +74,13 @@ __device__ __forceinline__ void copy_g2s(uint32_t dst, const void* src, uint32_t
 }
 }  // namespace bulk
 
-template <int N, int R, int D, int MINB>
+template <int N, int R, int D, int MINB, bool FUSED = false>
 __global__ void __launch_bounds__(kTmemThreads, MINB)
     twisted_tmem_v5_kernel(const WaypointParams prm, const TmemLaunchV5 tl, const __grid_constant__ CUtensorMap tmap) {
   constexpr int h = N / 2;
   constexpr int m = h - 1;
   constexpr int kL = m * (m + 1) / 2;
-  constexpr int kSlots = kL + m * D + D;
+  constexpr int kSlots = kL + m * D;  // no positions in the state: the input tile stays resident for the whole tile
   constexpr int kWords = 2 * kSlots;
   constexpr unsigned kFull = 0xffffffffu;
   constexpr int kWarps = kTmemThreads / 32;
@@ -82,16 +97,25 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
   const int M = (K + 1) >> 1;
   const int nh = half ? K - M - 1 : M - 1;
   const int nmax = M - 1;
-  const int ntm = tl.n_tmem_blocks;
+  const int tslots = tl.tmem_slots;
+  const int nbuf = tl.n_buffers;
 
   uint32_t* holder = reinterpret_cast<uint32_t*>(smem_raw);
   double2* stage = reinterpret_cast<double2*>(smem_raw + kTmemHeaderBytes) + size_t(warp) * 32 * (D * h);
   unsigned char* after_stage = smem_raw + kTmemHeaderBytes + size_t(kWarps) * tmem_stage_bytes_per_warp<N, D>();
   const uint32_t bar0 = tmem::smem_u32(after_stage) + uint32_t(warp) * 16;  // two 8-byte mbarriers per warp
-  const int tile_t = 16 * K, tile_f = 16 * D * nf, tile_doubles = tile_t + tile_f;
-  double* tiles = reinterpret_cast<double*>(after_stage + 128) + size_t(warp) * 2 * tile_doubles;
-  double* spill = reinterpret_cast<double*>(after_stage + 128) + size_t(kWarps) * 2 * tile_doubles + threadIdx.x;
-  auto SP = [&](int blk, int slot) -> double& { return spill[(size_t(blk) * kSlots + slot) * kTmemThreads]; };
+  // FUSED: the tile is the waypoint record positions[16][K+1][D]; segment times are computed from it
+  // (estimateSegmentTimesNfabian) and kept in a small per-thread history for the outward sweep
+  const int tile_t = FUSED ? 0 : 16 * K, tile_f = FUSED ? 16 * (K + 1) * D : 16 * D * nf, tile_doubles = tile_t + tile_f;
+  double* tiles = reinterpret_cast<double*>(after_stage + 128) + size_t(warp) * nbuf * tile_doubles;
+  double* spill = reinterpret_cast<double*>(after_stage + 128) + size_t(kWarps) * nbuf * tile_doubles + threadIdx.x;
+  double* thist = nullptr;  // FUSED only: behind the spilled state
+  if constexpr (FUSED) {
+    const int total_state = nmax * kSlots;
+    thist = spill + size_t(total_state > tslots ? total_state - tslots : 0) * kTmemThreads;
+  }
+  auto TH = [&](int j) -> double& { return thist[size_t(j) * kTmemThreads]; };
+  auto SPG = [&](int s_global) -> double& { return spill[size_t(s_global - tslots) * kTmemThreads]; };
 
   uint32_t tbase = 0;
   if (tl.tmem_cols > 0) {
@@ -101,34 +125,53 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
     tmem::fence_after_sync();
     tbase = *holder + (uint32_t(warp * 32) << 16);
   }
+  // State block `blk` occupies state doubles [blk*kSlots, (blk+1)*kSlots): entirely in TMEM, entirely in shared
+  // memory, or -- for the one block that straddles tmem_slots -- split slot by slot (all tests are warp-uniform).
   auto put_state = [&](int blk, const double (&sv)[kSlots]) {
-    if (blk < ntm) {
+    const int s0 = blk * kSlots;
+    if (s0 + kSlots <= tslots) {
 #pragma unroll
       for (int i = 0; i < kSlots; ++i) {
         const uint32_t w[2] = {(uint32_t)__double2loint(sv[i]), (uint32_t)__double2hiint(sv[i])};
-        tmem::st<2>(tbase + uint32_t(blk * kWords + 2 * i), w);
+        tmem::st<2>(tbase + uint32_t(2 * (s0 + i)), w);
       }
+    } else if (s0 >= tslots) {
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) SPG(s0 + i) = sv[i];
     } else {
 #pragma unroll
-      for (int i = 0; i < kSlots; ++i) SP(blk - ntm, i) = sv[i];
+      for (int i = 0; i < kSlots; ++i) {
+        if (s0 + i < tslots) {
+          const uint32_t w[2] = {(uint32_t)__double2loint(sv[i]), (uint32_t)__double2hiint(sv[i])};
+          tmem::st<2>(tbase + uint32_t(2 * (s0 + i)), w);
+        } else {
+          SPG(s0 + i) = sv[i];
+        }
+      }
     }
   };
-  // The tensor-memory read is asynchronous until tcgen05.wait::ld: state_issue() starts it, the caller does the
-  // work that does not depend on the state (segment time, its powers, E_v u_{v+1}), state_finish() waits.
-  auto state_issue = [&](int blk, uint32_t (&w)[kWords]) {
-    if (blk < ntm) tmem::ld_words<kWords>(tbase + uint32_t(blk * kWords), w);
-  };
-  auto state_finish = [&](int blk, const uint32_t (&w)[kWords], double (&sv)[kSlots]) {
-    if (blk < ntm) {
+  auto get_state = [&](int blk, double (&sv)[kSlots]) {
+    const int s0 = blk * kSlots;
+    if (s0 + kSlots <= tslots) {
+      uint32_t w[kWords];
+      tmem::ld_words<kWords>(tbase + uint32_t(2 * s0), w);
       tmem::wait_ld();
 #pragma unroll
       for (int i = 0; i < kSlots; ++i) sv[i] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
-    } else {
+    } else if (s0 >= tslots) {
 #pragma unroll
-      for (int i = 0; i < kSlots; ++i) sv[i] = SP(blk - ntm, i);
+      for (int i = 0; i < kSlots; ++i) sv[i] = SPG(s0 + i);
+    } else {
+      uint32_t w[kWords];
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i)
+        if (s0 + i < tslots) tmem::ld<2>(tbase + uint32_t(2 * (s0 + i)), &w[2 * i]);
+      tmem::wait_ld();
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i)
+        sv[i] = (s0 + i < tslots) ? __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]) : SPG(s0 + i);
     }
   };
-
 
   auto seg = [&](int j) -> int { return half ? K - 1 - j : j; };
   auto pidx = [&](int v) -> int {
@@ -158,8 +201,12 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
       const uint32_t bar = bar0 + 8u * buf;
       double* dst = tiles + size_t(buf) * tile_doubles;
       bulk::mbar_expect_tx(bar, uint32_t(tile_doubles) * 8u);
-      bulk::copy_g2s(tmem::smem_u32(dst), prm.times + w * 16 * K, uint32_t(tile_t) * 8u, bar);
-      bulk::copy_g2s(tmem::smem_u32(dst + tile_t), prm.dfix + w * 16 * (long long)D * nf, uint32_t(tile_f) * 8u, bar);
+      if constexpr (FUSED) {
+        bulk::copy_g2s(tmem::smem_u32(dst), prm.positions + w * 16 * (long long)(K + 1) * D, uint32_t(tile_f) * 8u, bar);
+      } else {
+        bulk::copy_g2s(tmem::smem_u32(dst), prm.times + w * 16 * K, uint32_t(tile_t) * 8u, bar);
+        bulk::copy_g2s(tmem::smem_u32(dst + tile_t), prm.dfix + w * 16 * (long long)D * nf, uint32_t(tile_f) * 8u, bar);
+      }
     }
   };
   if (wt < n_wtiles) fetch_tile(wt, 0);
@@ -169,20 +216,34 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
   const int tl_row = lane >> 1;  // this lane's trajectory inside the tile
 
   for (int it = 0; wt < n_wtiles; ++it) {
-    const int buf = it & 1;
-    // draw the next tile now and fetch it into the other buffer: a whole tile of lead.  The other buffer was read
-    // (generic proxy) by the previous tile; order those reads before the asynchronous-proxy write.
+    const int buf = nbuf == 2 ? (it & 1) : 0;
     long long wt_next = dyn ? __shfl_sync(kFull, pending, 0) : wt + wt_stride;
     if (dyn) pending = draw_tile();
-    fence_proxy_async();
-    __syncwarp();
-    if (wt_next < n_wtiles) fetch_tile(wt_next, buf ^ 1);
-    bulk::mbar_wait(bar0 + 8u * buf, uint32_t(it >> 1) & 1u);
+    if (nbuf == 2) {
+      // fetch the next tile into the other buffer now: a whole tile of lead.  That buffer was read (generic proxy) by
+      // the previous tile; order those reads before the asynchronous-proxy write.
+      fence_proxy_async();
+      __syncwarp();
+      if (wt_next < n_wtiles) fetch_tile(wt_next, buf ^ 1);
+    }
+    bulk::mbar_wait(bar0 + 8u * buf, nbuf == 2 ? (uint32_t(it >> 1) & 1u) : (uint32_t(it) & 1u));
 
     const double* __restrict__ tT = tiles + size_t(buf) * tile_doubles + tl_row * K;
-    const double* __restrict__ tF = tiles + size_t(buf) * tile_doubles + tile_t + tl_row * (D * nf);
-    auto in_T = [&](int j) -> double { return tT[seg(j)]; };
-    auto in_x = [&](int v, int d) -> double { return tF[d * nf + pidx(v)]; };
+    const double* __restrict__ tF =
+        tiles + size_t(buf) * tile_doubles + tile_t + tl_row * (FUSED ? (K + 1) * D : D * nf);
+    // time of own segment j: from the tile, or (FUSED) from the history filled by the inward sweep
+    auto in_T = [&](int j) -> double {
+      if constexpr (FUSED) return TH(j);
+      return tT[seg(j)];
+    };
+    auto in_x = [&](int v, int d) -> double {
+      if constexpr (FUSED) return tF[(half ? K - v : v) * D + d];
+      return tF[d * nf + pidx(v)];
+    };
+    auto in_u0 = [&](int b, int d) -> double {  // fixed end derivative b+1 of own vertex 0, own-frame sign
+      if constexpr (FUSED) return 0.0;
+      return sgn(b) * tF[d * nf + e0 + b];
+    };
     const long long traj0 = wt * 16;
     const long long traj = traj0 + tl_row;
 
@@ -250,7 +311,13 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
         xm[d] = in_x(0, d);
         xc[d] = in_x(1, d);
       }
-      const double T0 = in_T(0);
+      double T0;
+      if constexpr (FUSED) {
+        T0 = nfabian_time<D>(xm, xc, prm.v_max, prm.a_max, prm.magic);
+        TH(0) = T0;
+      } else {
+        T0 = in_T(0);
+      }
       if (!(T0 > 0.0)) stat |= kStatusBadTime;
       const double iT0 = fast_rcp(T0);
       double pw[N - 1];
@@ -269,7 +336,7 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
       for (int d = 0; d < D; ++d) {
         double u0[m];
 #pragma unroll
-        for (int b = 0; b < m; ++b) u0[b] = sgn(b) * tF[d * nf + e0 + b];
+        for (int b = 0; b < m; ++b) u0[b] = in_u0(b, d);
 #pragma unroll
         for (int a = 0; a < m; ++a) {
           double acc = 0.0;
@@ -287,7 +354,13 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
         double xn[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) xn[d] = in_x(v + 1, d);
-        const double T = in_T(v);
+        double T;
+        if constexpr (FUSED) {
+          T = nfabian_time<D>(xc, xn, prm.v_max, prm.a_max, prm.magic);
+          TH(v) = T;
+        } else {
+          T = in_T(v);
+        }
         if (!(T > 0.0)) stat |= kStatusBadTime;
         const double iT = fast_rcp(T);
         double pw[N - 1];
@@ -365,8 +438,6 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
           for (int j = 0; j < m; ++j)
 #pragma unroll
             for (int d = 0; d < D; ++d) sv[slot++] = yp[j][d];
-#pragma unroll
-          for (int d = 0; d < D; ++d) sv[slot++] = xc[d];
         }
 #pragma unroll
         for (int a = 0; a < m; ++a) {
@@ -385,7 +456,7 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
       put_state(v - 1, sv);
     }
     __syncwarp();
-    if (ntm > 0) tmem::wait_st();
+    if (tslots > 0) tmem::wait_st();
 
     // ---------------------------------------------------------------- middle vertex
     double um[m][D];
@@ -484,19 +555,18 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
 
     for (int v = nmax; v >= 1; --v) {
       double sv[kSlots];
-      {
-        uint32_t w[kWords];
-        state_issue(v - 1, w);
-        state_finish(v - 1, w, sv);
-      }
+      get_state(v - 1, sv);
       const bool act = v <= nh;
       double T = 1.0, iT = 1.0;
       double sd[h][D];
       if (act) {
         double xv[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) xv[d] = sv[kL + m * D + d];
+        for (int d = 0; d < D; ++d) xv[d] = in_x(v, d);
         T = in_T(v);
+        if constexpr (FUSED) {
+          if (prm.times_out != nullptr) prm.times_out[traj * K + seg(v)] = T;
+        }
         iT = fast_rcp(T);
         double pw[N - 1];
         segment_powers<N, R>(T, iT, pw);
@@ -564,10 +634,20 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
       for (int d = 0; d < D; ++d) {
         sd[0][d] = in_x(0, d);
 #pragma unroll
-        for (int b = 0; b < m; ++b) sd[1 + b][d] = sgn(b) * tF[d * nf + e0 + b];
+        for (int b = 0; b < m; ++b) sd[1 + b][d] = in_u0(b, d);
       }
       const double T = in_T(0);
+      if constexpr (FUSED) {
+        if (prm.times_out != nullptr) prm.times_out[traj * K + seg(0)] = T;
+      }
       const double iT = fast_rcp(T);
+      if (nbuf == 1) {
+        // single buffer: every input of this tile is in registers now -- refill it with the next tile while the last
+        // segment is emitted
+        fence_proxy_async();
+        __syncwarp();
+        if (wt_next < n_wtiles) fetch_tile(wt_next, 0);
+      }
       __syncwarp();
       emit_all(0, 0, T, iT, sd, ed);
     }

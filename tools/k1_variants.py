@@ -17,7 +17,7 @@ def main():
     dev = torch.device("cuda:0")
     s = m.Solver(0)
     cfgs = [("C3", 10, 4, 16, 3, 262144), ("C2", 10, 4, 8, 3, 65536), ("C4", 8, 3, 4, 3, 1048576),
-            ("K6", 10, 4, 6, 3, 262144), ("K2", 10, 4, 2, 3, 262144)]
+            ("C5x1", 10, 4, 16, 3, 1048576), ("K12", 10, 4, 12, 3, 262144)]
     # (variant, ring depth, CTA cap [9 = one CTA per tile], stagger us, dynamic tiles)
     # ring depth "2" selects the ring-depth-3 kernel WITHOUT the hoisted outward-sweep work (A/B of the hoist)
     variants = [(3, 0, 0, 0, 0), (4, 3, 0, 0, 1), (4, 3, 0, 0, 2), (6, 3, 0, 0, 1), (6, 3, 0, 0, 2)]
