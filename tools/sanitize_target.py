@@ -20,7 +20,7 @@ pos, times = O.make_waypoint_batch(K, D, B, base_seed=1000)
 ref, _ = O.solve_waypoint_batch(N, r, pos, times, n_threads=4)
 prob = m.Problem(N, r, K, D)
 t_d, f_d = torch.from_numpy(times).cuda(), torch.from_numpy(O.waypoint_d_fixed(N, pos)).cuda()
-for variant in ((2,) if NO_TMEM else (3, 4, 2)):
+for variant in ((2,) if NO_TMEM else (3, 4, 6, 5, 2)):
     s.set_option(m.capi.OPT_WAYPOINT_VARIANT, variant)
     st = torch.full((B,), -1, dtype=torch.int32, device="cuda")
     out = s.solve_linear(prob, t_d, f_d, status=st)
@@ -28,14 +28,15 @@ for variant in ((2,) if NO_TMEM else (3, 4, 2)):
     err = (np.abs(out.cpu().numpy() - ref).reshape(B, -1).max(1) / np.abs(ref).reshape(B, -1).max(1)).max()
     assert err < 1e-10 and bool((st == 0).all()), (variant, err)
 s.set_option(m.capi.OPT_WAYPOINT_VARIANT, 2 if NO_TMEM else 0)
+s.set_option(m.capi.OPT_MELLINGER_UNFUSED, 1 if NO_TMEM else 0)
 if not NO_TMEM:
     s.solve_waypoints_nfabian(N, r, torch.from_numpy(pos).cuda(), 3.0, 5.0, 6.5)
 cost = s.compute_cost(prob, t_d, out)
 ev = s.evaluate(t_d, out, 1, 0.0, 0.5, 33)
 c2, g2 = s.cost_gradient_mellinger(prob, t_d[:7].contiguous(), f_d[:7].contiguous())
-# K = 50 (large-K path) and an odd K
-for K2 in (50, 7):
-    p2, t2 = O.make_waypoint_batch(K2, D, 40, base_seed=3)
+# K = 50 (large-K path), an odd K, K = 8 with a multiple-of-16 batch (TMA-input kernel, double buffered)
+for K2 in (() if NO_TMEM else (50, 7, 8)):
+    p2, t2 = O.make_waypoint_batch(K2, D, 48, base_seed=3)
     s.solve_linear(m.Problem(N, r, K2, D), torch.from_numpy(t2).cuda(), torch.from_numpy(O.waypoint_d_fixed(N, p2)).cuda())
 # generic mask through the pinned 3-stream host pipeline
 h = N // 2
