@@ -184,9 +184,13 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
   const long long n_wtiles = prm.B >> 4;  // B is a multiple of 16 (host-checked)
   const long long wt_stride = (long long)gridDim.x * kWarps;
   const bool dyn = tl.tile_counter != nullptr;
-  auto draw_tile = [&]() -> long long { return lane == 0 ? (long long)atomicAdd(tl.tile_counter, 1ULL) : 0; };
-  // dynamic assignment draws TWO tiles ahead so that the atomic's round trip never sits in front of a fetch
-  long long wt = dyn ? __shfl_sync(kFull, draw_tile(), 0) : (long long)blockIdx.x * kWarps + warp;
+  // Dynamic assignment: the FIRST tile of every warp is its static one (no atomic in front of the first fetch); the
+  // counter hands out the tiles after those, and is always drawn one tile ahead of its use so that the atomic's
+  // round trip to L2 never sits in front of a fetch.
+  auto draw_tile = [&]() -> long long {
+    return lane == 0 ? (long long)atomicAdd(tl.tile_counter, 1ULL) + wt_stride : 0;
+  };
+  long long wt = (long long)blockIdx.x * kWarps + warp;
   long long pending = dyn ? draw_tile() : 0;  // lane 0 holds the tile after `wt`
 
   // one elected lane moves a whole tile: seg_times[16][K] and d_fixed[16][D][nf] are contiguous in global memory
