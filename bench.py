@@ -468,15 +468,17 @@ def run_ours(args):
         # ---- the same job with the gather FUSED into the solve: every rank's kernel stores its coefficients through
         # NVLink peer memory straight into the root's output (sharding.peer_solve_into_root); no collective
         try:
+            if not args.peer_store:
+                raise RuntimeError("skipped (enable with --peer-store)")
             if rank == 0:
                 o_root.zero_()
-            t_alias = sharding.share_from_root(t_root, 0)
-            f_alias = sharding.share_from_root(f_root, 0)
-            o_alias = sharding.share_from_root(o_root, 0)
+            t_pb = sharding.PeerBuffer(solver, t_root, 0)
+            f_pb = sharding.PeerBuffer(solver, f_root, 0)
+            o_pb = sharding.PeerBuffer(solver, o_root, 0)
             pbufs = {}
 
             def peer_step():
-                sharding.peer_solve_into_root(solve_fn, t_alias, f_alias, o_alias, total, dev, local_buffers=pbufs)
+                sharding.peer_solve_into_root(solver, prob, t_pb, f_pb, o_pb, total, dev, local_buffers=pbufs)
 
             for _ in range(3):
                 peer_step()
@@ -504,7 +506,10 @@ def run_ours(args):
                     "frac_of_nvlink_peer_peak": out_bytes / (peer_ms * 1e-3) / 1e9 / NVLINK_PEER_GBS,
                     "rows_bitwise_equal_local_solve": bool(torch.equal(chk, o_root[lo:hi])),
                     "results_finite": bool(torch.isfinite(o_root).all().item())}
-            del t_alias, f_alias, o_alias, pbufs
+            barrier()
+            for pb in (t_pb, f_pb, o_pb):
+                pb.close()
+            del pbufs
         except Exception as e:  # reported, never fails the bench
             if rank == 0 and sg is not None:
                 sg["fused_peer_store"] = {"failed": str(e)[:300]}
@@ -627,6 +632,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-configuration lines (N=1)")
     ap.add_argument("--no-scatter-gather", action="store_true")
+    ap.add_argument("--peer-store", action="store_true",
+                    help="also time the fused solve + gather over NVLink peer memory (CUDA IPC mapping of the root's output)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -212,7 +212,18 @@ void* mtg_device_alloc(mtg_handle* h, uint64_t bytes);
 void mtg_device_free(mtg_handle* h, void* ptr);
 int mtg_memcpy_h2d(mtg_handle* h, void* dst, const void* src, uint64_t bytes, void* stream);
 int mtg_memcpy_d2h(mtg_handle* h, void* dst, const void* src, uint64_t bytes, void* stream);
+int mtg_memcpy_d2d(mtg_handle* h, void* dst, const void* src, uint64_t bytes, void* stream);  /* incl. peer memory */
 int mtg_stream_synchronize(mtg_handle* h, void* stream);
+
+/* ---- NVLink peer memory between the one-process-per-GPU ranks of a job ----------------------------------------
+ * The owner exports a device buffer (64-byte CUDA IPC handle + offset of `ptr` inside its allocation), another
+ * rank imports it with ITS device current, which makes the buffer directly addressable by the kernels of that
+ * rank: handing a slice of the root's coefficient buffer to mtg_solve_linear_batch_f64 as `coeffs` makes the solve
+ * kernels store their results over NVLink straight into their final place -- the gather of BASELINE config C5
+ * fused into the solve (mav_trajectory_generation_b200/sharding.py:peer_solve_into_root). */
+int mtg_ipc_export(mtg_handle* h, const void* ptr, uint8_t handle_out[64], uint64_t* offset_out);
+int mtg_ipc_import(mtg_handle* h, const uint8_t handle[64], uint64_t offset, void** ptr_out, void** base_out);
+int mtg_ipc_close(mtg_handle* h, void* base);
 
 /* library version (major*10000 + minor*100 + patch) */
 int mtg_version(void);

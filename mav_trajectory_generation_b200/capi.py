@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "mtg_solve_waypoints_nfabian_batch_f64", "mtg_solve_waypoints_nfabian_batch_host_f64",
     "mtg_cost_gradient_mellinger_batch_f64", "mtg_evaluate_batch_f64", "mtg_evaluate_range_batch_f64",
     "mtg_cost_gradient_mellinger_batch_host_f64", "mtg_evaluate_range_batch_host_f64",
+    "mtg_memcpy_d2d", "mtg_ipc_export", "mtg_ipc_import", "mtg_ipc_close",
 ]
 
 
@@ -80,6 +81,10 @@ def load():
     L.mtg_memcpy_h2d.argtypes = [vp, vp, vp, C.c_uint64, vp]
     L.mtg_memcpy_d2h.argtypes = [vp, vp, vp, C.c_uint64, vp]
     L.mtg_stream_synchronize.argtypes = [vp, vp]
+    L.mtg_memcpy_d2d.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    L.mtg_ipc_export.argtypes = [vp, vp, C.c_char_p, C.POINTER(C.c_uint64)]
+    L.mtg_ipc_import.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(vp), C.POINTER(vp)]
+    L.mtg_ipc_close.argtypes = [vp, vp]
     L.mtg_version.restype = C.c_int
     L.mtg_set_option.argtypes = [vp, C.c_int, C.c_int]
     L.mtg_evaluate_batch_f64.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i64, dp, dp, C.c_int32, C.c_double,
@@ -173,6 +178,31 @@ class Solver:
             status.data_ptr() if status is not None else None, s)
         self._check(rc, "mtg_solve_linear_batch_f64")
         return coeffs
+
+    # ---- raw device pointers (peer memory imported with ipc_import has no torch tensor behind it) ----
+    def solve_linear_ptr(self, prob, B, seg_times_ptr, d_fixed_ptr, coeffs_ptr, stream):
+        rc = self.lib.mtg_solve_linear_batch_f64(self.h, C.byref(prob.c), int(B), int(seg_times_ptr), int(d_fixed_ptr),
+                                                 int(coeffs_ptr), None, None, int(stream))
+        self._check(rc, "mtg_solve_linear_batch_f64")
+
+    def memcpy_d2d(self, dst_ptr, src_ptr, nbytes, stream):
+        self._check(self.lib.mtg_memcpy_d2d(self.h, int(dst_ptr), int(src_ptr), int(nbytes), int(stream)), "mtg_memcpy_d2d")
+
+    def ipc_export(self, tensor):
+        """(handle bytes [64], offset) of a CUDA tensor's storage position, for ipc_import on another rank."""
+        buf = C.create_string_buffer(64)
+        off = C.c_uint64(0)
+        self._check(self.lib.mtg_ipc_export(self.h, tensor.data_ptr(), buf, C.byref(off)), "mtg_ipc_export")
+        return bytes(buf.raw), int(off.value)
+
+    def ipc_import(self, handle, offset):
+        """-> (pointer to the exported position, base pointer to pass to ipc_close)."""
+        ptr, base = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.mtg_ipc_import(self.h, handle, int(offset), C.byref(ptr), C.byref(base)), "mtg_ipc_import")
+        return int(ptr.value), int(base.value)
+
+    def ipc_close(self, base):
+        self._check(self.lib.mtg_ipc_close(self.h, int(base)), "mtg_ipc_close")
 
     def solve_waypoints_nfabian(self, N, r, positions, v_max, a_max, magic=6.5, coeffs=None, seg_times_out=None,
                                 status=None, stream=None):

@@ -1619,6 +1619,63 @@ int mtg_memcpy_d2h(mtg_handle* h, void* dst, const void* src, uint64_t bytes, vo
   MTG_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return MTG_OK;
 }
+int mtg_memcpy_d2d(mtg_handle* h, void* dst, const void* src, uint64_t bytes, void* stream) {
+  if (!h) return MTG_ERR_BAD_ARG;
+  DeviceGuard g(h->device);
+  MTG_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return MTG_OK;
+}
+
+// ---- peer memory (NVLink): export / import a device allocation between the one-process-per-GPU ranks ----------
+int mtg_ipc_export(mtg_handle* h, const void* ptr, uint8_t handle_out[64], uint64_t* offset_out) {
+  if (!h || !ptr || !handle_out || !offset_out) return MTG_ERR_BAD_ARG;
+  DeviceGuard g(h->device);
+  typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static const RangeFn range = []() -> RangeFn {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<RangeFn>(fp);
+  }();
+  if (!range) {
+    h->error = "cuMemGetAddressRange is not available from the driver";
+    return MTG_ERR_CUDA;
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (range(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS) {
+    h->error = "cuMemGetAddressRange failed";
+    return MTG_ERR_CUDA;
+  }
+  cudaIpcMemHandle_t hd;
+  MTG_CUDA(h, cudaIpcGetMemHandle(&hd, reinterpret_cast<void*>(base)));
+  static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(handle_out, &hd, 64);
+  *offset_out = uint64_t(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  return MTG_OK;
+}
+
+int mtg_ipc_import(mtg_handle* h, const uint8_t handle[64], uint64_t offset, void** ptr_out, void** base_out) {
+  if (!h || !handle || !ptr_out || !base_out) return MTG_ERR_BAD_ARG;
+  DeviceGuard g(h->device);  // opened with THIS handle's device current: peer access to the owner is enabled lazily
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle, 64);
+  void* base = nullptr;
+  MTG_CUDA(h, cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+  *base_out = base;
+  *ptr_out = static_cast<char*>(base) + offset;
+  return MTG_OK;
+}
+
+int mtg_ipc_close(mtg_handle* h, void* base) {
+  if (!h || !base) return MTG_ERR_BAD_ARG;
+  DeviceGuard g(h->device);
+  MTG_CUDA(h, cudaIpcCloseMemHandle(base));
+  return MTG_OK;
+}
+
 int mtg_stream_synchronize(mtg_handle* h, void* stream) {
   if (!h) return MTG_ERR_BAD_ARG;
   DeviceGuard g(h->device);

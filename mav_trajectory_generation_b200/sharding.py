@@ -117,46 +117,69 @@ def solve_scattered(solve_fn, times_root, dfix_root, total, K, D, N, n_fixed, de
 # the following tiles continues.  The transfer overlaps the math tile by tile inside ONE kernel; there is no gather
 # step, no staging copy and no NCCL call on the data path (torch.distributed only carries the 64-byte IPC handle
 # once, and the barrier).  Inputs go the other way with one DMA per rank (peer copy of its contiguous slice).
+# The mapping is opened through the C-ABI (mtg_ipc_import) with the RANK's device current, which is what makes the
+# root's memory addressable from this rank's kernels (torch's own IPC rebuild opens it under the owner's device).
 
-def share_from_root(tensor, root=0):
-    """Collective: returns, on every rank, a tensor aliasing `tensor` of rank `root` (the root gets its own tensor
-    back).  The root's tensor must stay alive for as long as the aliases are used."""
-    from torch.multiprocessing.reductions import reduce_tensor
-    rank = dist.get_rank()
-    payload = [reduce_tensor(tensor) if rank == root else None]
-    dist.broadcast_object_list(payload, src=root)
-    if rank == root:
-        return tensor
-    fn, args = payload[0]
-    alias = fn(*args)
-    # make sure this process has peer access from its compute device to the root's device enabled (torch enables it
-    # lazily on the first cross-device copy)
-    probe = torch.empty(1, dtype=alias.dtype, device=torch.device("cuda", torch.cuda.current_device()))
-    probe.copy_(alias.reshape(-1)[:1])
-    torch.cuda.synchronize()
-    return alias
+_ipc_open = {}  # IPC handle bytes -> [base pointer, reference count]: a handle may be opened once per process
 
 
-def peer_solve_into_root(solve_fn, times_alias, dfix_alias, out_alias, total, device, root=0, local_buffers=None):
-    """One step of the fused path.  times_alias / dfix_alias / out_alias come from share_from_root (on the root they
-    are the root's own tensors).  Every rank copies its input slice with one peer DMA each, then solves straight
-    into its slice of the root's output.  The caller brackets steps with a barrier + synchronize."""
+class PeerBuffer:
+    """A device buffer of rank `root`, addressable from this rank: `.ptr` is a raw device pointer (the root's own
+    tensor on the root, an NVLink peer mapping elsewhere).  Keep the root tensor alive while mappings exist."""
+
+    def __init__(self, solver, tensor, root=0):
+        rank = dist.get_rank()
+        payload = [solver.ipc_export(tensor) if rank == root else None]
+        dist.broadcast_object_list(payload, src=root)
+        self.solver = solver
+        self.tensor = tensor if rank == root else None
+        self.base = None
+        if rank == root:
+            self.ptr = tensor.data_ptr()
+        else:
+            handle, offset = payload[0]
+            ent = _ipc_open.get(handle)
+            if ent is None:  # opened with THIS rank's device current
+                _, base = solver.ipc_import(handle, 0)
+                ent = _ipc_open[handle] = [base, 0]
+            ent[1] += 1
+            self.base, self.handle = ent[0], handle
+            self.ptr = ent[0] + offset
+
+    def close(self):
+        if self.base is not None:
+            ent = _ipc_open[self.handle]
+            ent[1] -= 1
+            if ent[1] == 0:
+                self.solver.ipc_close(ent[0])
+                del _ipc_open[self.handle]
+            self.base = None
+
+
+def peer_solve_into_root(solver, prob, times_pb, dfix_pb, out_pb, total, device, root=0, local_buffers=None):
+    """One step of the fused path: every rank pulls its input slice from the root with one peer DMA per array, then
+    solves with `coeffs` pointing INTO the root's output buffer (PeerBuffer) -- the kernels' TMA stores are the
+    gather.  The caller brackets steps with a barrier + synchronize."""
     world, rank = dist.get_world_size(), dist.get_rank()
     bounds = shard_bounds(total, world)
     lo, hi = bounds[rank], bounds[rank + 1]
-    if hi <= lo:
+    n = hi - lo
+    if n <= 0:
         return
+    K, D, N, nf = prob.K, prob.D, prob.N, prob.n_fixed
+    stream = torch.cuda.current_stream(device).cuda_stream
+    out_ptr = out_pb.ptr + lo * K * D * N * 8
     if rank == root:
-        solve_fn(times_alias[lo:hi], dfix_alias[lo:hi], out_alias[lo:hi])
+        solver.solve_linear_ptr(prob, n, times_pb.ptr + lo * K * 8, dfix_pb.ptr + lo * D * nf * 8, out_ptr, stream)
         return
     buf = local_buffers if local_buffers is not None else {}
-    if buf.get("n") != hi - lo:
-        buf["t"] = torch.empty((hi - lo,) + tuple(times_alias.shape[1:]), dtype=torch.float64, device=device)
-        buf["f"] = torch.empty((hi - lo,) + tuple(dfix_alias.shape[1:]), dtype=torch.float64, device=device)
-        buf["n"] = hi - lo
-    buf["t"].copy_(times_alias[lo:hi], non_blocking=True)   # peer DMA, NVLink
-    buf["f"].copy_(dfix_alias[lo:hi], non_blocking=True)
-    solve_fn(buf["t"], buf["f"], out_alias[lo:hi])           # TMA stores land in the root's HBM
+    if buf.get("n") != n:
+        buf["t"] = torch.empty((n, K), dtype=torch.float64, device=device)
+        buf["f"] = torch.empty((n, D, nf), dtype=torch.float64, device=device)
+        buf["n"] = n
+    solver.memcpy_d2d(buf["t"].data_ptr(), times_pb.ptr + lo * K * 8, n * K * 8, stream)          # peer DMA, NVLink
+    solver.memcpy_d2d(buf["f"].data_ptr(), dfix_pb.ptr + lo * D * nf * 8, n * D * nf * 8, stream)
+    solver.solve_linear_ptr(prob, n, buf["t"].data_ptr(), buf["f"].data_ptr(), out_ptr, stream)    # stores land at the root
 
 
 # ---- host side: NUMA placement of a rank's pinned buffers ------------------------------------------------

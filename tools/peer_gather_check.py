@@ -21,6 +21,7 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
     solver = m.Solver(local)
+    peer_variant = int(os.environ.get("MTG_PEER_VARIANT", "-1"))  # diagnostic: force a kernel for the peer-store path
     ok = True
     for N, r, K, D, total in ((10, 4, 16, 3, 20011), (10, 4, 8, 3, 4096), (10, 4, 50, 3, 1000)):
         prob = m.Problem(N, r, K, D)
@@ -35,11 +36,16 @@ def main():
         def solve_fn(t, f, c):
             solver.solve_linear(prob, t, f, coeffs=c)
 
-        t_a = sharding.share_from_root(times, 0)
-        f_a = sharding.share_from_root(dfix, 0)
-        o_a = sharding.share_from_root(out_peer, 0)
-        sharding.peer_solve_into_root(solve_fn, t_a, f_a, o_a, total, dev)
+        if peer_variant >= 0:
+            solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, peer_variant)
+        t_pb = sharding.PeerBuffer(solver, times, 0)
+        f_pb = sharding.PeerBuffer(solver, dfix, 0)
+        o_pb = sharding.PeerBuffer(solver, out_peer, 0)
+        sharding.peer_solve_into_root(solver, prob, t_pb, f_pb, o_pb, total, dev)
         torch.cuda.synchronize()
+        solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, 0)
+        if rank == 1:
+            print(f"rank 1: peer-store solve K={K} completed (variant {peer_variant})", flush=True)
         dist.barrier()
         sharding.scatter_solve_gather(solve_fn, times, dfix, out_nccl, total, K, D, N, prob.n_fixed, dev, chunks=3)
         torch.cuda.synchronize()
@@ -49,7 +55,8 @@ def main():
             a, b = bool(torch.equal(out_peer, want)), bool(torch.equal(out_nccl, want))
             print(f"K={K} total={total}: peer-store path bitwise {a}, NCCL path bitwise {b}")
             ok = ok and a and b
-        del t_a, f_a, o_a
+        for pb in (t_pb, f_pb, o_pb):
+            pb.close()
         dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
