@@ -14,7 +14,10 @@ the per-trajectory configuration is the headline C3's).  Prints ONE JSON line (r
   scatter_gather (N>1)  the full BASELINE C5 data path: rank 0 holds the batch; chunked, full-duplex NCCL
              send/recv of the inputs out and the coefficients back, overlapped with the solves
              (mav_trajectory_generation_b200/sharding.py); root NVLink ingest GB/s against the measured
-             770 GB/s peer-copy figure of B200_PROFILING.md.
+             770 GB/s peer-copy figure of B200_PROFILING.md.  Two NVLink peer-memory forms of the same job
+             are timed beside it: `fused_peer_store` (every rank's solve kernel TMA-stores its coefficients
+             into the root's output, no gather step) and `peer_dma_pipeline` (copy engines pull the inputs
+             and push the coefficients, chunked over three streams); `best_path` names the fastest.
   e2e        same metric through the host-pointer C-ABI call (what
              PolynomialOptimization<N>::solveLinear() / BatchPolynomialOptimization calls):
              pinned HOST buffers (bound to the GPU's NUMA node), H2D + kernels + D2H inside the timed region.
@@ -468,8 +471,8 @@ def run_ours(args):
         # ---- the same job with the gather FUSED into the solve: every rank's kernel stores its coefficients through
         # NVLink peer memory straight into the root's output (sharding.peer_solve_into_root); no collective
         try:
-            if not args.peer_store:
-                raise RuntimeError("skipped (enable with --peer-store)")
+            if args.no_peer_paths:
+                raise RuntimeError("skipped (--no-peer-paths)")
             if rank == 0:
                 o_root.zero_()
             t_pb = sharding.PeerBuffer(solver, t_root, 0)
@@ -506,13 +509,61 @@ def run_ours(args):
                     "frac_of_nvlink_peer_peak": out_bytes / (peer_ms * 1e-3) / 1e9 / NVLINK_PEER_GBS,
                     "rows_bitwise_equal_local_solve": bool(torch.equal(chk, o_root[lo:hi])),
                     "results_finite": bool(torch.isfinite(o_root).all().item())}
+            # ---- and with the copy engines doing the exchange: chunked pull / solve / push pipeline on three streams
+            # (sharding.peer_dma_solve_gather); full-size NVLink write packets, no SM time spent on the transfer
+            barrier()
+            if rank == 0:
+                o_root.zero_()
+            dbufs = {}
+            by_chunks = {}
+            for n_chunks in (args.chunks, 2 * args.chunks, 4 * args.chunks):
+                def dma_step():
+                    sharding.peer_dma_solve_gather(solver, prob, t_pb, f_pb, o_pb, total, dev, chunks=n_chunks,
+                                                   local_buffers=dbufs)
+
+                for _ in range(3):
+                    dma_step()
+                barrier()
+                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t_w0 = time.perf_counter()
+                d0.record()
+                for _ in range(sg_steps):
+                    dma_step()
+                d1.record()
+                barrier()
+                wall_ms = allmax((time.perf_counter() - t_w0) * 1e3) / sg_steps
+                by_chunks[n_chunks] = (allmax(d0.elapsed_time(d1)) / sg_steps, wall_ms)
+            best_chunks = min(by_chunks, key=lambda c: by_chunks[c][0])
+            dma_ms, dma_wall_ms = by_chunks[best_chunks]
+            if rank == 0:
+                sg["peer_dma_pipeline"] = {
+                    "what": "copy engines do the exchange: per rank a 3-stream pipeline over `chunks` pieces -- peer DMA "
+                            "pull of the inputs, local solve, peer DMA push of the coefficients into their final place "
+                            "in the root's output; no collective, no SM time on the transfer",
+                    "ms_per_step": dma_ms, "ms_per_step_wall_incl_barrier": dma_wall_ms, "chunks": best_chunks,
+                    "ms_per_step_by_chunks": {str(c): v[0] for c, v in by_chunks.items()},
+                    "value": total / (dma_ms * 1e-3), "unit": UNIT,
+                    "root_ingress_GBps": out_bytes / (dma_ms * 1e-3) / 1e9,
+                    "frac_of_nvlink_peer_peak": out_bytes / (dma_ms * 1e-3) / 1e9 / NVLINK_PEER_GBS,
+                    "rows_bitwise_equal_local_solve": bool(torch.equal(chk, o_root[lo:hi])),
+                    "results_finite": bool(torch.isfinite(o_root).all().item())}
+            del dbufs
             barrier()
             for pb in (t_pb, f_pb, o_pb):
                 pb.close()
             del pbufs
         except Exception as e:  # reported, never fails the bench
             if rank == 0 and sg is not None:
-                sg["fused_peer_store"] = {"failed": str(e)[:300]}
+                sg["peer_dma_pipeline" if "fused_peer_store" in sg else "fused_peer_store"] = {"failed": str(e)[:300]}
+        if rank == 0 and sg is not None:
+            paths = {"nccl_pipeline": sg["ms_per_step"]}
+            for key in ("fused_peer_store", "peer_dma_pipeline"):
+                if isinstance(sg.get(key), dict) and "ms_per_step" in sg[key]:
+                    paths[key] = sg[key]["ms_per_step"]
+            best = min(paths, key=paths.get)
+            sg["best_path"] = best
+            sg["best_ms_per_step"] = paths[best]
+            sg["best_frac_of_nvlink_peer_peak"] = out_bytes / (paths[best] * 1e-3) / 1e9 / NVLINK_PEER_GBS
         if world > 1:
             dist.barrier()
         del t_root, f_root, o_root, bufs
@@ -632,8 +683,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-configuration lines (N=1)")
     ap.add_argument("--no-scatter-gather", action="store_true")
-    ap.add_argument("--peer-store", action="store_true",
-                    help="also time the fused solve + gather over NVLink peer memory (CUDA IPC mapping of the root's output)")
+    ap.add_argument("--peer-store", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--no-peer-paths", action="store_true",
+                    help="skip the two NVLink peer-memory variants of the C5 data path (fused solve + gather through TMA "
+                         "stores into the root's output; copy-engine pull / solve / push pipeline)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

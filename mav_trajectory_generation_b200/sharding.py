@@ -182,6 +182,59 @@ def peer_solve_into_root(solver, prob, times_pb, dfix_pb, out_pb, total, device,
     solver.solve_linear_ptr(prob, n, buf["t"].data_ptr(), buf["f"].data_ptr(), out_ptr, stream)    # stores land at the root
 
 
+def peer_dma_solve_gather(solver, prob, times_pb, dfix_pb, out_pb, total, device, root=0, chunks=4,
+                          local_buffers=None):
+    """Scatter / solve / gather with the copy engines doing the exchange (no collective, no SM time spent on the
+    transfer): every rank cuts its slice into `chunks` pieces and runs a three-stream pipeline
+        copy-in stream : peer DMA PULL of piece c's inputs from the root
+        compute stream : solve piece c into a local buffer (full-rate local TMA stores)
+        copy-out stream: peer DMA PUSH of piece c's coefficients into their final place in the root's output
+    so the root's NVLink ingress carries full-size write packets from all peers while the solves and the input pulls
+    overlap it.  The root solves its own slice in place.  Events order the three streams; the call returns with
+    everything joined on the current stream (the caller brackets steps with a barrier + synchronize)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    bounds = shard_bounds(total, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    n = hi - lo
+    if n <= 0:
+        return
+    K, D, N, nf = prob.K, prob.D, prob.N, prob.n_fixed
+    cur = torch.cuda.current_stream(device)
+    if rank == root:
+        solver.solve_linear_ptr(prob, n, times_pb.ptr + lo * K * 8, dfix_pb.ptr + lo * D * nf * 8,
+                                out_pb.ptr + lo * K * D * N * 8, cur.cuda_stream)
+        return
+    buf = local_buffers if local_buffers is not None else {}
+    if buf.get("n") != n or "c" not in buf:
+        buf["t"] = torch.empty((n, K), dtype=torch.float64, device=device)
+        buf["f"] = torch.empty((n, D, nf), dtype=torch.float64, device=device)
+        buf["c"] = torch.empty((n, K, D, N), dtype=torch.float64, device=device)
+        buf["n"] = n
+    if "s_in" not in buf:
+        buf["s_in"], buf["s_out"] = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    s_in, s_out = buf["s_in"], buf["s_out"]
+    s_in.wait_stream(cur)   # the previous step's solves have read the input buffers
+    s_out.wait_stream(cur)
+    b = chunk_bounds(0, n, chunks)
+    row_t, row_f, row_c = K * 8, D * nf * 8, K * D * N * 8
+    for c in range(chunks):
+        a, e = b[c], b[c + 1]
+        if e <= a:
+            continue
+        solver.memcpy_d2d(buf["t"].data_ptr() + a * row_t, times_pb.ptr + (lo + a) * row_t, (e - a) * row_t, s_in.cuda_stream)
+        solver.memcpy_d2d(buf["f"].data_ptr() + a * row_f, dfix_pb.ptr + (lo + a) * row_f, (e - a) * row_f, s_in.cuda_stream)
+        ev_in = torch.cuda.Event()
+        ev_in.record(s_in)
+        cur.wait_event(ev_in)
+        solver.solve_linear_ptr(prob, e - a, buf["t"].data_ptr() + a * row_t, buf["f"].data_ptr() + a * row_f,
+                                buf["c"].data_ptr() + a * row_c, cur.cuda_stream)
+        ev_solved = torch.cuda.Event()
+        ev_solved.record(cur)
+        s_out.wait_event(ev_solved)
+        solver.memcpy_d2d(out_pb.ptr + (lo + a) * row_c, buf["c"].data_ptr() + a * row_c, (e - a) * row_c, s_out.cuda_stream)
+    cur.wait_stream(s_out)
+
+
 # ---- host side: NUMA placement of a rank's pinned buffers ------------------------------------------------
 
 def gpu_numa_node(index):

@@ -1,5 +1,6 @@
-"""Multi-GPU data paths on real GPUs (skipped on a single-GPU box): the NCCL scatter/solve/gather pipeline and the
-fused solve + gather over NVLink peer memory both reproduce a single-GPU solve bit for bit (tools/peer_gather_check.py)."""
+"""Multi-GPU data paths on real GPUs (skipped on a single-GPU box): the NCCL scatter/solve/gather pipeline, the fused
+solve + gather over NVLink peer memory and the copy-engine pull / solve / push pipeline all reproduce a single-GPU
+solve bit for bit (tools/peer_gather_check.py)."""
 import os
 import socket
 import subprocess

@@ -29,9 +29,10 @@ def main():
             times, dfix = synth(N, K, D, total, dev, seed=3)
             out_peer = torch.zeros((total, K, D, N), dtype=torch.float64, device=dev)
             out_nccl = torch.zeros((total, K, D, N), dtype=torch.float64, device=dev)
+            out_dma = torch.zeros((total, K, D, N), dtype=torch.float64, device=dev)
             want = solver.solve_linear(prob, times, dfix)
         else:
-            times = dfix = out_peer = out_nccl = want = None
+            times = dfix = out_peer = out_nccl = out_dma = want = None
 
         def solve_fn(t, f, c):
             solver.solve_linear(prob, t, f, coeffs=c)
@@ -44,6 +45,11 @@ def main():
         sharding.peer_solve_into_root(solver, prob, t_pb, f_pb, o_pb, total, dev)
         torch.cuda.synchronize()
         solver.set_option(m.capi.OPT_WAYPOINT_VARIANT, 0)
+        d_pb = sharding.PeerBuffer(solver, out_dma, 0)
+        dbufs = {}
+        for _ in range(2):  # twice: the second step reuses the buffers and streams of the first
+            sharding.peer_dma_solve_gather(solver, prob, t_pb, f_pb, d_pb, total, dev, chunks=3, local_buffers=dbufs)
+        torch.cuda.synchronize()
         if rank == 1:
             print(f"rank 1: peer-store solve K={K} completed (variant {peer_variant})", flush=True)
         dist.barrier()
@@ -52,10 +58,10 @@ def main():
         dist.barrier()
         if rank == 0:
             torch.cuda.synchronize()
-            a, b = bool(torch.equal(out_peer, want)), bool(torch.equal(out_nccl, want))
-            print(f"K={K} total={total}: peer-store path bitwise {a}, NCCL path bitwise {b}")
-            ok = ok and a and b
-        for pb in (t_pb, f_pb, o_pb):
+            a, b, c = bool(torch.equal(out_peer, want)), bool(torch.equal(out_nccl, want)), bool(torch.equal(out_dma, want))
+            print(f"K={K} total={total}: peer-store path bitwise {a}, NCCL path bitwise {b}, peer-DMA pipeline bitwise {c}")
+            ok = ok and a and b and c
+        for pb in (t_pb, f_pb, o_pb, d_pb):
             pb.close()
         dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=dev)
