@@ -110,6 +110,8 @@ int mtg_device_is_sm100(const mtg_handle* h);
 #define MTG_OPT_MELLINGER_UNFUSED 8 /* 1 = batched Mellinger gradient through expand + solve + cost kernels */
 #define MTG_OPT_TMA_INPUTS 9      /* 0 = never, 1 = the TMA-input kernel (v5) where two input tiles fit (double buffered),
                                     2 (default) = also where only one fits (single buffered) */
+#define MTG_OPT_EARLY_REFILL 10   /* TMA-input kernel with one tile buffer: 0 = the buffer is refilled with the next tile two
+                                   * outward-sweep steps before the tile ends (default), -1 = while the last segment is emitted */
 #define MTG_OPT_DYNAMIC_TILES 5   /* persistent kernel: warps draw tiles from a global counter: 0 = auto, 1 = always, 2 = never */
 int mtg_set_option(mtg_handle* h, int key, int value);
 

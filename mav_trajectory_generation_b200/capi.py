@@ -18,6 +18,8 @@ OPT_WAYPOINT_VARIANT = 1
 OPT_RING_DEPTH, OPT_CTAS_PER_SM, OPT_STAGGER_US, OPT_DYNAMIC_TILES, OPT_CHUNK_BLOCKS = 2, 3, 4, 5, 6
 OPT_GENERIC_VARIANT = 7
 OPT_MELLINGER_UNFUSED = 8
+OPT_TMA_INPUTS = 9
+OPT_EARLY_REFILL = 10
 
 EXPORTED_SYMBOLS = [
     "mtg_create", "mtg_destroy", "mtg_last_error", "mtg_launch_count", "mtg_device_is_sm100",

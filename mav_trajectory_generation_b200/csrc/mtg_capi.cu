@@ -50,6 +50,7 @@ struct mtg_handle {
   int64_t launches = 0;
   int waypoint_variant = 0;  // MTG_OPT_WAYPOINT_VARIANT
   int ring_depth = 3;        // MTG_OPT_RING_DEPTH (v4 kernel: cp.async input ring buffers, 2..4)
+  int early_steps = 0;       // MTG_OPT_EARLY_REFILL (v5, single tile buffer): 0 = on (kV5Early steps of lead), -1 = off
   int ctas_per_sm = 0;       // MTG_OPT_CTAS_PER_SM (v4 kernel: 0 = as many as fit, 9 = one CTA per tile, not persistent)
   int stagger_us = 0;        // MTG_OPT_STAGGER_US (v4 kernel: CTA start times spread over this many microseconds)
   int tma_inputs = 2;        // MTG_OPT_TMA_INPUTS (default routing prefers the TMA-input kernel v5 when eligible)
@@ -238,12 +239,17 @@ constexpr int kV4MaxK = 8;
 
 // ---- v5: v4 with the inputs moved by TMA bulk copies (whole 16-trajectory tiles, double buffered); K <= 8
 typedef void (*V5Kernel)(const mtg::WaypointParams, const mtg::TmemLaunchV5, const CUtensorMap);
+// lead (outward-sweep steps) of the single-buffer tile refill: measured on C3 / C5-on-one-GPU / K = 14 with E = off, 1, 2, 3,
+// 4 -> 0.625 / 0.638 / 0.646 / 0.641 / 0.639 (C3), 0.657 / 0.679 / 0.690 / 0.671 / 0.663 (C5x1)  [tools/early_refill_sweep.py]
+constexpr int kV5Early = 2;
 struct V5Entry {
   int N, R, D;
   V5Kernel fn, fn_fused;
+  V5Kernel fn_early, fn_fused_early;  // the EARLY = kV5Early instantiations
 };
-#define MTG_V5(N_, R_, D_, MB_) \
-  {N_, R_, D_, mtg::twisted_tmem_v5_kernel<N_, R_, D_, MB_, false>, mtg::twisted_tmem_v5_kernel<N_, R_, D_, MB_, true>}
+#define MTG_V5(N_, R_, D_, MB_)                                                                                       \
+  {N_, R_, D_, mtg::twisted_tmem_v5_kernel<N_, R_, D_, MB_, false>, mtg::twisted_tmem_v5_kernel<N_, R_, D_, MB_, true>, \
+   mtg::twisted_tmem_v5_kernel<N_, R_, D_, MB_, false, kV5Early>, mtg::twisted_tmem_v5_kernel<N_, R_, D_, MB_, true, kV5Early>}
 const V5Entry kV5Kernels[] = {MTG_V5(10, 4, 3, 2), MTG_V5(8, 3, 3, 3),  MTG_V5(10, 4, 1, 2),
                               MTG_V5(10, 3, 3, 2), MTG_V5(10, 2, 3, 2), MTG_V5(12, 5, 3, 2)};
 const V5Entry* find_v5(const mtg_problem* p) {
@@ -706,6 +712,21 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
           tl.tmem_cols = best_cols;
           tl.n_buffers = best_nbuf;
           tl.tile_counter = nullptr;
+          V5Kernel launch_fn = fn5;
+          if (best_nbuf == 1 && h->early_steps >= 0) {
+            // early refill of the single tile buffer (EARLY instantiation): both lanes must own >= E vertices and the
+            // parking area must lie in tensor memory behind the state blocks still needed
+            const int E = kV5Early;
+            const int own_min = p->K - (p->K + 1) / 2 - 1;
+            const int stash = (p->D + 1) * E + p->D + mm * p->D + 1;
+            const V5Kernel fe = fused ? e5->fn_fused_early : e5->fn_early;
+            if (fe != nullptr && E <= own_min && E <= nmax && E * kslots + stash <= best_cols / 2) {
+              int regs_e = 0;
+              const int rc_regs = kernel_regs(h, (const void*)fe, &regs_e);
+              if (rc_regs != MTG_OK) return rc_regs;
+              if (65536 / (std::max(regs_e, 1) * mtg::kTmemThreads) >= best_ctas) launch_fn = fe;
+            }
+          }
           const int64_t blocks = std::min<int64_t>((B + 63) / 64, int64_t(best_ctas) * h->sm_count);
           // dynamic tile counter for long tiles with several tiles per warp (balances the tail: C3 0.618 vs 0.605,
           // C5 on one GPU 0.655 vs 0.630); static round-robin for short trajectories, where the atomic's round trip is
@@ -717,7 +738,7 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
             MTG_CUDA(h, cudaMemsetAsync(tl.tile_counter, 0, sizeof(unsigned long long), stream));
           }
           {
-            const int rc_smem = ensure_dyn_smem(h, (const void*)fn5, best_smem);
+            const int rc_smem = ensure_dyn_smem(h, (const void*)launch_fn, best_smem);
             if (rc_smem != MTG_OK) return rc_smem;
           }
           CUtensorMap tmap;
@@ -725,7 +746,7 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
             const int rc = encode_coeff_tmap(h, &tmap, coeffs, B, p);
             if (rc != MTG_OK) return rc;
           }
-          fn5<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl, tmap);
+          launch_fn<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl, tmap);
           MTG_CUDA(h, cudaGetLastError());
           h->launches++;
           return MTG_OK;
@@ -1048,6 +1069,10 @@ int mtg_set_option(mtg_handle* h, int key, int value) {
   }
   if (key == MTG_OPT_WAYPOINT_VARIANT && value >= 0 && value <= 6) {
     h->waypoint_variant = value;
+    return MTG_OK;
+  }
+  if (key == MTG_OPT_EARLY_REFILL && value >= -1 && value <= 0) {
+    h->early_steps = value;
     return MTG_OK;
   }
   if (key == MTG_OPT_RING_DEPTH && value >= 2 && value <= 4) {

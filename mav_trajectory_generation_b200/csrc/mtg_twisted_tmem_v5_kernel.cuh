@@ -25,8 +25,9 @@ struct TmemLaunchV5 {
                     // granularity: state double number s (block * 22 + slot at N = 10, D = 3) lives in TMEM when
                     // s < tmem_slots, in shared memory otherwise
   int tmem_cols;
-  int n_buffers;    // input tiles per warp: 2 = next tile fetched a whole tile ahead (K <= 8), 1 = fetched while the
-                    // last segment is emitted (the state of longer trajectories leaves room for one tile only)
+  int n_buffers;    // input tiles per warp: 2 = next tile fetched a whole tile ahead (K <= 12 at N = 10, D = 3), 1 = the
+                    // state of longer trajectories leaves room for one tile only: refilled during the outward sweep
+                    // (EARLY template parameter) or while the last segment is emitted
   unsigned long long* tile_counter;  // non-null: dynamic tile assignment
 };
 
@@ -74,7 +75,17 @@ __device__ __forceinline__ void copy_g2s(uint32_t dst, const void* src, uint32_t
 }
 }  // namespace bulk
 
-template <int N, int R, int D, int MINB, bool FUSED = false>
+// EARLY = E > 0 (single tile buffer only): when the outward sweep reaches own vertex E, what its last E steps and the
+// closing step still read from the tile ((D+1)*E + D + m*D + 1 doubles per lane) is parked in tensor-memory slots of
+// state blocks that are already popped (blocks >= E), and the tile buffer is refilled with the next tile there and
+// then: E back-substitution + emission steps of lead for the fetch instead of one.  The host launches this
+// instantiation only when n_buffers == 1, both lanes own >= E vertices, and the parking area lies inside tensor memory.
+template <int N, int D>
+__host__ __device__ constexpr int v5_early_stash_slots(int E) {
+  return (D + 1) * E + D + (N / 2 - 1) * D + 1;
+}
+
+template <int N, int R, int D, int MINB, bool FUSED = false, int EARLY = 0>
 __global__ void __launch_bounds__(kTmemThreads, MINB)
     twisted_tmem_v5_kernel(const WaypointParams prm, const TmemLaunchV5 tl, const __grid_constant__ CUtensorMap tmap) {
   constexpr int h = N / 2;
@@ -187,8 +198,12 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
   // Dynamic assignment: the FIRST tile of every warp is its static one (no atomic in front of the first fetch); the
   // counter hands out the tiles after those, and is always drawn one tile ahead of its use so that the atomic's
   // round trip to L2 never sits in front of a fetch.
+  // (inline PTX: the compiler turns atomicAdd() under `lane == 0` into its warp-aggregated form, ATOMG followed at once
+  // by a SHFL of the result -- which puts the round trip back in front of the warp: 2.4 % of all stall samples)
   auto draw_tile = [&]() -> long long {
-    return lane == 0 ? (long long)atomicAdd(tl.tile_counter, 1ULL) + wt_stride : 0;
+    unsigned long long old = 0;
+    if (lane == 0) asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(old) : "l"(tl.tile_counter) : "memory");
+    return (long long)old + wt_stride;
   };
   long long wt = (long long)blockIdx.x * kWarps + warp;
   long long pending = dyn ? draw_tile() : 0;  // lane 0 holds the tile after `wt`
@@ -557,7 +572,34 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
     }
     if (half == 0) store_free(nh + 1, ed);
 
+    constexpr int kStash0 = EARLY * kSlots;  // state slots of the blocks >= EARLY: popped when the sweep reaches vertex EARLY
+    auto park = [&](int slot, double val) {
+      const uint32_t w[2] = {(uint32_t)__double2loint(val), (uint32_t)__double2hiint(val)};
+      tmem::st<2>(tbase + uint32_t(2 * (kStash0 + slot)), w);
+    };
     for (int v = nmax; v >= 1; --v) {
+      if constexpr (EARLY > 0) {
+        if (v == EARLY) {
+          // park what steps EARLY..1 and the closing step read from the tile, then refill the tile buffer now
+#pragma unroll
+          for (int u = EARLY; u >= 1; --u) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) park((EARLY - u) * (D + 1) + d, in_x(u, d));
+            park((EARLY - u) * (D + 1) + D, in_T(u));
+          }
+#pragma unroll
+          for (int d = 0; d < D; ++d) park(EARLY * (D + 1) + d, in_x(0, d));
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+#pragma unroll
+            for (int b = 0; b < m; ++b) park(EARLY * (D + 1) + D + d * m + b, in_u0(b, d));
+          park(EARLY * (D + 1) + D + m * D, in_T(0));
+          tmem::wait_st();
+          fence_proxy_async();
+          __syncwarp();
+          if (wt_next < n_wtiles) fetch_tile(wt_next, 0);
+        }
+      }
       double sv[kSlots];
       get_state(v - 1, sv);
       const bool act = v <= nh;
@@ -565,9 +607,18 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
       double sd[h][D];
       if (act) {
         double xv[D];
+        if (EARLY > 0 && v <= EARLY) {
+          uint32_t w[2 * (D + 1)];
+          tmem::ld_words<2 * (D + 1)>(tbase + uint32_t(2 * (kStash0 + (EARLY - v) * (D + 1))), w);
+          tmem::wait_ld();
 #pragma unroll
-        for (int d = 0; d < D; ++d) xv[d] = in_x(v, d);
-        T = in_T(v);
+          for (int d = 0; d < D; ++d) xv[d] = __hiloint2double((int)w[2 * d + 1], (int)w[2 * d]);
+          T = __hiloint2double((int)w[2 * D + 1], (int)w[2 * D]);
+        } else {
+#pragma unroll
+          for (int d = 0; d < D; ++d) xv[d] = in_x(v, d);
+          T = in_T(v);
+        }
         if constexpr (FUSED) {
           if (prm.times_out != nullptr) prm.times_out[traj * K + seg(v)] = T;
         }
@@ -634,18 +685,34 @@ __global__ void __launch_bounds__(kTmemThreads, MINB)
     }
     {
       double sd[h][D];
+      double T;
+      if constexpr (EARLY > 0) {
+        constexpr int kClose = D + m * D + 1;
+        uint32_t w[2 * kClose];
+        tmem::ld_words<2 * kClose>(tbase + uint32_t(2 * (kStash0 + EARLY * (D + 1))), w);
+        tmem::wait_ld();
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        sd[0][d] = in_x(0, d);
+        for (int d = 0; d < D; ++d) {
+          sd[0][d] = __hiloint2double((int)w[2 * d + 1], (int)w[2 * d]);
 #pragma unroll
-        for (int b = 0; b < m; ++b) sd[1 + b][d] = in_u0(b, d);
+          for (int b = 0; b < m; ++b)
+            sd[1 + b][d] = __hiloint2double((int)w[2 * (D + d * m + b) + 1], (int)w[2 * (D + d * m + b)]);
+        }
+        T = __hiloint2double((int)w[2 * (kClose - 1) + 1], (int)w[2 * (kClose - 1)]);
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          sd[0][d] = in_x(0, d);
+#pragma unroll
+          for (int b = 0; b < m; ++b) sd[1 + b][d] = in_u0(b, d);
+        }
+        T = in_T(0);
       }
-      const double T = in_T(0);
       if constexpr (FUSED) {
         if (prm.times_out != nullptr) prm.times_out[traj * K + seg(0)] = T;
       }
       const double iT = fast_rcp(T);
-      if (nbuf == 1) {
+      if (EARLY == 0 && nbuf == 1) {
         // single buffer: every input of this tile is in registers now -- refill it with the next tile while the last
         // segment is emitted
         fence_proxy_async();
