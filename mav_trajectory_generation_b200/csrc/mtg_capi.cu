@@ -1302,10 +1302,28 @@ int mtg_evaluate_range_batch_f64(mtg_handle* h, int32_t N, int32_t K, int32_t D,
     h->launches++;
   }
   if (max_samples > 0) {
-    const int threads = 256;
+    // block size: the output tile (threads * n_derivs * D doubles) stays under 40 KB of shared memory
+    const int rec = n_derivs * D;
+    if (size_t(32) * rec * 8 > size_t(160) * 1024) {
+      h->error = "mtg_evaluate_range_batch_f64: n_derivs * D too large for the output tile";
+      arena_release(h, ar, s);
+      return MTG_ERR_BAD_ARG;
+    }
+    const int threads = std::max(32, std::min(256, int((40 * 1024) / (rec * 8)) / 32 * 32));
+    const size_t smem = size_t(threads) * rec * sizeof(double);
+    typedef void (*RangeEval)(const mtg::RangeParams);
+    static const RangeEval kRangeEval[MTG_MAX_N] = {
+        mtg::range_eval_kernel<1>, mtg::range_eval_kernel<2>,  mtg::range_eval_kernel<3>,  mtg::range_eval_kernel<4>,
+        mtg::range_eval_kernel<5>, mtg::range_eval_kernel<6>,  mtg::range_eval_kernel<7>,  mtg::range_eval_kernel<8>,
+        mtg::range_eval_kernel<9>, mtg::range_eval_kernel<10>, mtg::range_eval_kernel<11>, mtg::range_eval_kernel<12>};
+    const RangeEval fn = kRangeEval[N - 1];
+    {
+      const int rc_smem = ensure_dyn_smem(h, (const void*)fn, smem);
+      if (rc_smem != MTG_OK) return rc_smem;
+    }
     const int64_t total = B * int64_t(max_samples);
     const int64_t blocks = std::min<int64_t>((total + threads - 1) / threads, int64_t(h->sm_count) * 32);
-    mtg::range_eval_kernel<<<(unsigned)blocks, threads, 0, s>>>(rp);
+    fn<<<(unsigned)blocks, threads, smem, s>>>(rp);
     MTG_CUDA(h, cudaGetLastError());
     h->launches++;
   }
