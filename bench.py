@@ -322,6 +322,26 @@ def widened_rows(torch, m, solver, dev, peak):
                                  "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak}
     except Exception as e:
         out["evaluate_range"] = {"failed": str(e)}
+    try:  # computeCost() of solved trajectories and Trajectory::evaluate on a uniform grid
+        N, r, K, D, B, S = 10, 4, 16, 3, 262144, 64
+        prob = m.Problem(N, r, K, D)
+        _, times, dfix = synth_batch(torch, N, K, D, B, dev, seed=13)
+        coeffs = solver.solve_linear(prob, times, dfix)
+        cost = torch.empty((B,), dtype=torch.float64, device=dev)
+        ms = _time_launches(torch, lambda: solver.compute_cost(prob, times, coeffs, cost=cost), 5, warmup=2)
+        nbytes = B * (8 * K + 8 * K * D * N + 8)
+        out["compute_cost"] = {"workload": f"computeCost() of {B} solved C3 trajectories", "ms": ms,
+                               "trajectories_per_s": B / (ms * 1e-3), "achieved_GBps": nbytes / (ms * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak}
+        t_end = float(times.sum(dim=1).min().item())
+        ms = _time_launches(torch, lambda: solver.evaluate(times, coeffs, 1, 0.0, t_end / S, S), 5, warmup=2)
+        nbytes = B * (8 * K + 8 * K * D * N + 8 * S * D)
+        out["evaluate_uniform_grid"] = {"workload": f"Trajectory::evaluate (velocity) of {B} C3 trajectories on {S} grid points",
+                                        "ms": ms, "samples_per_s": B * S / (ms * 1e-3),
+                                        "achieved_GBps": nbytes / (ms * 1e-3) / 1e9,
+                                        "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak}
+    except Exception as e:
+        out["compute_cost"] = {"failed": str(e)}
     return out
 
 

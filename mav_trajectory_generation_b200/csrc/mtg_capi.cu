@@ -1213,9 +1213,32 @@ int mtg_compute_cost_batch_f64(mtg_handle* h, const mtg_problem* p, int64_t B, c
   prm.times = seg_times;
   prm.coeffs = coeffs;
   prm.cost = cost;
-  const int threads = 128;
-  int64_t blocks = std::min<int64_t>((B + threads - 1) / threads, int64_t(h->sm_count) * 16);
-  mtg::cost_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(prm);
+  const int threads = 256;
+  const int KD = p->K * p->D;
+  const int tpb = std::max(1, threads / KD);
+  const size_t smem = (size_t(36) + size_t(tpb) * KD) * sizeof(double);
+  if (smem > h->smem_optin) {
+    h->error = "mtg_compute_cost_batch_f64: K * D too large";
+    return MTG_ERR_BAD_ARG;
+  }
+  typedef void (*CostFn)(const mtg::CostParams, const int);
+  struct CostEntry {
+    int N, r;
+    CostFn fn;
+  };
+  static const CostEntry kCost[] = {{10, 4, mtg::cost_kernel<10, 4>}, {10, 3, mtg::cost_kernel<10, 3>},
+                                    {10, 2, mtg::cost_kernel<10, 2>}, {8, 3, mtg::cost_kernel<8, 3>},
+                                    {12, 5, mtg::cost_kernel<12, 5>}, {12, 4, mtg::cost_kernel<12, 4>},
+                                    {6, 2, mtg::cost_kernel<6, 2>},   {4, 1, mtg::cost_kernel<4, 1>}};
+  CostFn fn = mtg::cost_kernel<0, 0>;
+  for (const auto& e : kCost)
+    if (e.N == p->N && e.r == p->r) fn = e.fn;
+  {
+    const int rc_smem = ensure_dyn_smem(h, (const void*)fn, smem);
+    if (rc_smem != MTG_OK) return rc_smem;
+  }
+  int64_t blocks = std::min<int64_t>((B + tpb - 1) / tpb, int64_t(h->sm_count) * 16);
+  fn<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(prm, tpb);
   MTG_CUDA(h, cudaGetLastError());
   h->launches++;
   return MTG_OK;
@@ -1244,10 +1267,25 @@ int mtg_evaluate_batch_f64(mtg_handle* h, int32_t N, int32_t K, int32_t D, int64
   ep.times = seg_times;
   ep.coeffs = coeffs;
   ep.out = out;
-  const int threads = 256;
+  if (size_t(32) * D * 8 > size_t(160) * 1024) {
+    h->error = "mtg_evaluate_batch_f64: D too large for the output tile";
+    return MTG_ERR_BAD_ARG;
+  }
+  const int threads = std::max(32, std::min(256, int((40 * 1024) / (D * 8)) / 32 * 32));
+  const size_t smem = size_t(threads) * D * sizeof(double);
+  typedef void (*EvalFn)(const mtg::EvalParams);
+  static const EvalFn kEval[MTG_MAX_N] = {
+      mtg::evaluate_kernel<1>, mtg::evaluate_kernel<2>,  mtg::evaluate_kernel<3>,  mtg::evaluate_kernel<4>,
+      mtg::evaluate_kernel<5>, mtg::evaluate_kernel<6>,  mtg::evaluate_kernel<7>,  mtg::evaluate_kernel<8>,
+      mtg::evaluate_kernel<9>, mtg::evaluate_kernel<10>, mtg::evaluate_kernel<11>, mtg::evaluate_kernel<12>};
+  const EvalFn fn = kEval[N - 1];
+  {
+    const int rc_smem = ensure_dyn_smem(h, (const void*)fn, smem);
+    if (rc_smem != MTG_OK) return rc_smem;
+  }
   const int64_t total = B * int64_t(n_samples);
   const int64_t blocks = std::min<int64_t>((total + threads - 1) / threads, int64_t(h->sm_count) * 32);
-  mtg::evaluate_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(ep);
+  fn<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(ep);
   MTG_CUDA(h, cudaGetLastError());
   h->launches++;
   return MTG_OK;

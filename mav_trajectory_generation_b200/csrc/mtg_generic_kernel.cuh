@@ -306,42 +306,88 @@ struct EvalParams {
   double* __restrict__ out;           // [B][n_samples][D]
 };
 
+// Compile-time polynomial order (host switch) and derivative order (warp-uniform switch): base coefficients are
+// immediates; results leave through a shared-memory tile as coalesced stores (dynamic shared memory: [blockDim.x][D]).
+template <int N, int DER>
+__device__ __forceinline__ double eval_horner_fused(const double (&c)[N], double t) {
+  double acc = 0.0;
+  if constexpr (DER < N) {
+#pragma unroll
+    for (int j = N - 1; j >= DER; --j) {
+      double bc = 1.0;  // B(der, j) = j!/(j-der)!
+#pragma unroll
+      for (int q = 0; q < DER; ++q) bc *= double(j - q);
+      acc = fma(acc, t, bc * c[j]);
+    }
+  }
+  return acc;
+}
+template <int N>
+__device__ __forceinline__ double eval_horner_fused_any(const double (&c)[N], double t, int der) {
+  switch (der) {  // warp-uniform
+    case 0: return eval_horner_fused<N, 0>(c, t);
+    case 1: return eval_horner_fused<N, 1>(c, t);
+    case 2: return eval_horner_fused<N, 2>(c, t);
+    case 3: return eval_horner_fused<N, 3>(c, t);
+    case 4: return eval_horner_fused<N, 4>(c, t);
+    case 5: return eval_horner_fused<N, 5>(c, t);
+    case 6: return eval_horner_fused<N, 6>(c, t);
+    case 7: return eval_horner_fused<N, 7>(c, t);
+    case 8: return eval_horner_fused<N, 8>(c, t);
+    case 9: return eval_horner_fused<N, 9>(c, t);
+    case 10: return eval_horner_fused<N, 10>(c, t);
+    case 11: return eval_horner_fused<N, 11>(c, t);
+    default: return 0.0;
+  }
+}
+
+template <int N>
 __global__ void __launch_bounds__(256) evaluate_kernel(const EvalParams prm) {
-  const int N = prm.N, K = prm.K, D = prm.D, S = prm.n_samples, der = prm.derivative;
+  extern __shared__ double eval_tile[];
+  const int K = prm.K, D = prm.D, S = prm.n_samples, der = prm.derivative;
   const long long total = prm.B * S;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
-    const long long b = idx / S;
-    const int sidx = int(idx - b * S);
-    const double t = prm.t_start + sidx * prm.dt;
-    const double* __restrict__ tt = prm.times + b * K;
-    double start = 0.0;
-    int i = 0;
-    for (; i < K; ++i) {
-      const double Ti = tt[i];
-      if (start + Ti > t) break;
-      start += Ti;
-    }
-    bool in_range = true;
-    if (i == K) {
-      if (t > start) in_range = false;
-      i = K - 1;
-      start -= tt[i];
-    }
-    const double tl = t - start;
-    double* __restrict__ o = prm.out + idx * D;
-    for (int d = 0; d < D; ++d) {
-      double acc = 0.0;
-      if (in_range && der < N) {
-        const double* __restrict__ c = prm.coeffs + ((b * K + i) * D + d) * N;
-        for (int j = N - 1; j >= der; --j) {
-          double bc = 1.0;  // B(der, j) = j!/(j-der)!
-          for (int q = 0; q < der; ++q) bc *= double(j - q);
-          acc = fma(acc, tl, bc * c[j]);
-        }
+  const long long n_tiles = (total + blockDim.x - 1) / blockDim.x;
+  for (long long ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+    const long long idx0 = ti * blockDim.x;
+    const long long idx = idx0 + threadIdx.x;
+    if (idx < total) {
+      const long long b = idx / S;
+      const int sidx = int(idx - b * S);
+      const double t = prm.t_start + sidx * prm.dt;
+      const double* __restrict__ tt = prm.times + b * K;
+      double start = 0.0;
+      int i = 0;
+      for (; i < K; ++i) {
+        const double Ti = tt[i];
+        if (start + Ti > t) break;
+        start += Ti;
       }
-      o[d] = acc;
+      bool in_range = true;
+      if (i == K) {
+        if (t > start) in_range = false;
+        i = K - 1;
+        start -= tt[i];
+      }
+      const double tl = t - start;
+      double* __restrict__ o = eval_tile + threadIdx.x * D;
+      for (int d = 0; d < D; ++d) {
+        double acc = 0.0;
+        if (in_range) {
+          const double* __restrict__ cg = prm.coeffs + ((b * K + i) * D + d) * N;
+          double c[N];
+#pragma unroll
+          for (int j = 0; j < N; ++j) c[j] = cg[j];
+          acc = eval_horner_fused_any<N>(c, tl, der);
+        }
+        o[d] = acc;
+      }
     }
+    __syncthreads();
+    const long long left = total - idx0;
+    const int n_out = int(left < (long long)blockDim.x ? left : (long long)blockDim.x) * D;
+    double* __restrict__ og = prm.out + idx0 * D;
+    for (int k = threadIdx.x; k < n_out; k += blockDim.x) og[k] = eval_tile[k];
+    __syncthreads();
   }
 }
 
@@ -545,30 +591,81 @@ struct CostParams {
   double* __restrict__ cost;
 };
 
-__global__ void __launch_bounds__(128) cost_kernel(const CostParams prm) {
-  const int N = prm.N, r = prm.r, K = prm.K, D = prm.D;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
-  for (long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x; traj < prm.B; traj += nthreads) {
-    double total = 0.0;
-    for (int i = 0; i < K; ++i) {
-      const double T = prm.times[traj * K + i];
-      for (int d = 0; d < D; ++d) {
-        const double* __restrict__ c = prm.coeffs + ((traj * K + i) * D + d) * N;
-        double q[2 * MTG_MAX_N_HALF];
+// Work item = (trajectory, segment, dimension): its N coefficients are contiguous and consecutive items are contiguous,
+// so a block reads one contiguous span of the coefficient tensor (the thread-per-trajectory form walked 3 840-byte
+// rows with a 3 840-byte stride between lanes and kept q[] in local memory).  The per-item sum is the reference-order
+// double loop; the trajectory's total is then accumulated by ONE thread in (segment, dimension) order with the same
+// fma, so the result is bitwise what the thread-per-trajectory kernel produced.
+// dynamic shared memory: [12] B(r,a), [24] 1/k, [tpb * K * D] per-item sums   (tpb = trajectories per block pass)
+// NT, RT > 0: compile-time order / derivative (the double loop is (N-r)^2 fused multiply-adds with immediate 1/k);
+// NT = 0: any (N, r) with predicated 12 x 12 loops.
+template <int NT, int RT>
+__global__ void __launch_bounds__(256) cost_kernel(const CostParams prm, const int tpb) {
+  extern __shared__ double cost_sm[];
+  double* bcoef = cost_sm;
+  double* inv = cost_sm + 12;
+  double* partial = cost_sm + 36;
+  const int N = NT > 0 ? NT : prm.N, r = NT > 0 ? RT : prm.r, K = prm.K, D = prm.D, KD = K * D;
+  if (threadIdx.x < 12) {
+    double bc = 1.0;  // B(r,a) = a!/(a-r)!
+    for (int k = 0; k < r; ++k) bc *= double(int(threadIdx.x) - k);
+    bcoef[threadIdx.x] = bc;
+  }
+  if (threadIdx.x < 24) inv[threadIdx.x] = threadIdx.x ? 1.0 / double(threadIdx.x) : 0.0;
+  __syncthreads();
+  for (long long t0 = (long long)blockIdx.x * tpb; t0 < prm.B; t0 += (long long)gridDim.x * tpb) {
+    const int ntraj = int(prm.B - t0 < tpb ? prm.B - t0 : tpb);
+    const int items = ntraj * KD;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int lt = it / KD, i = (it - lt * KD) / D;
+      const double T = prm.times[(t0 + lt) * K + i];
+      const double* __restrict__ c = prm.coeffs + (t0 * KD + it) * N;
+      double sum = 0.0;
+      if constexpr (NT > 0) {
+        double q[NT];
         double tpow = 1.0;
-        for (int a = r; a < N; ++a) {
-          double bc = 1.0;  // B(r,a) = a!/(a-r)!
-          for (int k = 0; k < r; ++k) bc *= double(a - k);
-          q[a] = bc * c[a] * tpow;
+#pragma unroll
+        for (int a = RT; a < NT; ++a) {
+          q[a] = bcoef[a] * c[a] * tpow;
           tpow *= T;
         }
-        double s = 0.0;
-        for (int a = r; a < N; ++a)
-          for (int b = r; b < N; ++b) s = fma(q[a] * q[b], 1.0 / double(a + b - 2 * r + 1), s);
-        total = fma(s, T, total);  // 0.5 * 2 * T^(1) * sum
+#pragma unroll
+        for (int a = RT; a < NT; ++a)
+#pragma unroll
+          for (int b = RT; b < NT; ++b) sum = fma(q[a] * q[b], 1.0 / double(a + b - 2 * RT + 1), sum);
+      } else {
+        double q[12];
+        double tpow = 1.0;
+#pragma unroll
+        for (int a = 0; a < 12; ++a) {
+          q[a] = 0.0;
+          if (a >= r && a < N) {
+            q[a] = bcoef[a] * c[a] * tpow;
+            tpow *= T;
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 12; ++a) {
+          if (a >= r && a < N) {
+#pragma unroll
+            for (int b = 0; b < 12; ++b)
+              if (b >= r && b < N) sum = fma(q[a] * q[b], inv[a + b - 2 * r + 1], sum);
+          }
+        }
       }
+      partial[it] = sum;
     }
-    prm.cost[traj] = total;
+    __syncthreads();
+    if (threadIdx.x < ntraj) {
+      const long long traj = t0 + threadIdx.x;
+      double total = 0.0;
+      for (int i = 0; i < K; ++i) {
+        const double T = prm.times[traj * K + i];
+        for (int d = 0; d < D; ++d) total = fma(partial[threadIdx.x * KD + i * D + d], T, total);  // 0.5 * 2 * T * sum
+      }
+      prm.cost[traj] = total;
+    }
+    __syncthreads();
   }
 }
 
