@@ -50,8 +50,11 @@ CONFIGS = {
     "C3": (10, 4, 16, 3, 262144),
     "C2": (10, 4, 8, 3, 65536),
     "C4": (8, 3, 4, 3, 1048576),
-    "K50": (10, 4, 50, 3, 65536),
-    "K100": (10, 4, 100, 3, 32768),
+    # large K (reference timing program sizes): batches of ~3 GB of coefficients, a multiple of the 18 944 trajectories
+    # one pass of the persistent grid covers, so that the line shows the kernel and not the wave quantisation of a
+    # small batch (65 536 x K=50: 0.393, 32 768 x K=100: 0.340; tools/k_sweep.py)
+    "K50": (10, 4, 50, 3, 246272),
+    "K100": (10, 4, 100, 3, 113664),
 }
 METRIC = "min-snap trajectories/sec (N=10, 16-seg, 3D)"
 UNIT = "trajectories/s"

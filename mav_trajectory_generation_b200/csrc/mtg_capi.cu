@@ -528,7 +528,8 @@ int launch_masked(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int
     const int rem = p->D - d0;
     const int dg = rem > 4 ? (rem == 5 ? 3 : 4) : rem;  // 5 = 3 + 2 rather than 4 + 1
     MaskedKernel fn = kMaskedKernels[p->N / 2 - 1][dg - 1];
-    const size_t smem = size_t(4) * 32 * dg * p->N * sizeof(double);
+    const int kslots = hh * (hh + 1) / 2 + hh * dg;
+    const size_t smem = size_t(4) * 32 * dg * p->N * sizeof(double);  // staging tiles of the four warps
     {
         const int rc_smem = ensure_dyn_smem(h, (const void*)fn, size_t(smem));
         if (rc_smem != MTG_OK) return rc_smem;
@@ -537,7 +538,6 @@ int launch_masked(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int
     MTG_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, 128, smem));
     per_sm = std::max(per_sm, 1);
     const int64_t blocks = std::min<int64_t>((B + 127) / 128, int64_t(per_sm) * h->sm_count);
-    const int kslots = hh * (hh + 1) / 2 + hh * dg;
     const size_t bytes = size_t(p->K + 1) * kslots * size_t(blocks) * 128 * sizeof(double);
     int rc = arena_acquire(h, ar, bytes, stream);
     if (rc != MTG_OK) return rc;
