@@ -428,6 +428,15 @@ def run_ours(args):
     for _ in range(warm):
         solver.solve_linear(prob, times, dfix, coeffs=coeffs, status=status)
     barrier()
+    # a GPU that has just left idle may still be ramping its clocks after three 1 ms steps: keep warming (untimed) until
+    # 0.25 s of work has run; the count is reported as warmup_effective
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < 0.25:
+        for _ in range(8):
+            solver.solve_linear(prob, times, dfix, coeffs=coeffs, status=status)
+        torch.cuda.synchronize()
+        warm += 8
+    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -657,7 +666,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(8 * B * K * D * N + 4 * B), "steps": e2e_steps,
                     "bitwise_equal_to_device_path": e2e_ok, "bytes_are": "per GPU",
                     "numa_node_of_pinned_buffers": numa_node},
-            "gpu_launches": int(launches), "clocks": clocks, "results_ok": ok,
+            "gpu_launches": int(launches), "warmup_effective": int(warm), "clocks": clocks, "results_ok": ok,
             "fused_waypoint_entry_traj_per_s_rank0": fused_value,
             "wall_s_timed_region": t_wall,
         }

@@ -30,6 +30,16 @@ for variant in ((2,) if NO_TMEM else (3, 4, 6, 5, 2)):
 s.set_option(m.capi.OPT_WAYPOINT_VARIANT, 2 if NO_TMEM else 0)
 s.set_option(m.capi.OPT_MELLINGER_UNFUSED, 1 if NO_TMEM else 0)
 if not NO_TMEM:
+    # default routing on a multiple-of-16 batch larger than one pass of the persistent grid: the TMA-input kernel with
+    # one tile buffer, its early refill (mbarrier + cp.async.bulk + parked TMEM slots) and the dynamic tile counter
+    Bb = 40000
+    tb = t_d[torch.arange(Bb, device="cuda") % B].contiguous()
+    fb = f_d[torch.arange(Bb, device="cuda") % B].contiguous()
+    ob = s.solve_linear(prob, tb, fb)
+    torch.cuda.synchronize()
+    assert torch.equal(ob[:B], ob[B:2 * B]) and float((ob[:B] - out).abs().max()) < 1e-6
+    o_r, n_r, _ = s.evaluate_range(t_d, out, 0.0, float(t_d.sum(dim=1).min()), 0.37, derivs=(0, 1, 2), max_samples=64)
+if not NO_TMEM:
     s.solve_waypoints_nfabian(N, r, torch.from_numpy(pos).cuda(), 3.0, 5.0, 6.5)
 cost = s.compute_cost(prob, t_d, out)
 ev = s.evaluate(t_d, out, 1, 0.0, 0.5, 33)
