@@ -21,7 +21,8 @@ def launches(src, dst):
     total = sum(sum(v) for v in per.values())
     with open(dst, "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised launches)\n")
-        f.write("# command: python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras (first 60 launches: torch input synthesis, 13 headline launches of 1 048 576 trajectories [~1.1 ms each], then the chunked launches of the e2e host pipeline [32 768 trajectories each] -- hence the mixed average)\n")
+        f.write("# command: python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras, first 60 kernel launches of the process: "
+                "torch input synthesis, then headline launches of 1 048 576 trajectories each (warm-up and timed steps are the same launch)\n")
         f.write(f"{'kernel':92s} {'launches':>8s} {'avg_us':>10s} {'total_us':>10s} {'share':>7s}\n")
         for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"{k:92s} {len(v):8d} {sum(v)/len(v):10.2f} {sum(v):10.1f} {100*sum(v)/total:6.1f}%\n")
