@@ -94,3 +94,15 @@ def test_no_cpu_fallback():
     p = m.Problem(10, 4, 2, 3)
     assert lib.mtg_solve_linear_batch_f64(None, C.byref(p.c), 1, None, None, None, None, None, None) != 0
     assert lib.mtg_solve_linear_batch_host_f64(None, C.byref(p.c), 1, None, None, None, None, None) != 0
+
+
+def test_option_constants_match_the_header():
+    """capi.OPT_* are the MTG_OPT_* of include/mtg_b200.h (the Python binding restates them by hand)."""
+    import re
+    text = open(os.path.join(ROOT, "include", "mtg_b200.h")).read()
+    header = {name: int(val) for name, val in re.findall(r"#define\s+MTG_OPT_(\w+)\s+(\d+)", text)}
+    assert header, "no MTG_OPT_ definitions found"
+    values = sorted(header.values())
+    assert len(set(values)) == len(values), "duplicate option keys in the header"
+    for name, val in header.items():
+        assert getattr(capi, "OPT_" + name) == val, name
