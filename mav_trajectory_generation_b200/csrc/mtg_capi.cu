@@ -58,7 +58,6 @@ struct mtg_handle {
   int generic_variant = 0;   // MTG_OPT_GENERIC_VARIANT (0 = masked block kernel, 1 = banded kernel in global scratch)
   int chunk_blocks = 0;      // MTG_OPT_CHUNK_BLOCKS (chunked kernel: resident vertex blocks per lane, 0 = auto)
   int dynamic_tiles = 0;     // MTG_OPT_DYNAMIC_TILES (v4 kernel: warps draw tiles from a global counter)
-  unsigned long long* tile_counters = nullptr;  // one per pipeline slot (+ caller stream)
   std::vector<CachedTopology> topologies;
   // host-pointer pipeline
   static constexpr int kPipe = 3;
@@ -74,6 +73,8 @@ struct mtg_handle {
   };
   Arena scratch[kPipe + 1];  // generic kernel: banded factor + right-hand sides
   Arena pack[kPipe + 1];     // times + d_fixed produced by nfabian_pack_kernel; Mellinger expansion
+  Arena counters[kPipe + 1]; // dynamic tile counter of the persistent kernels (event-ordered like the scratch arenas: two
+                             // launches of one slot on different caller streams must not share a live counter)
   // cached launch plans of the TMEM kernel (per waypoint entry and K): attributes are set once
   struct TmemPlan {
     const void* entry = nullptr;
@@ -328,6 +329,16 @@ int arena_release(mtg_handle* h, mtg_handle::Arena& a, cudaStream_t stream) {
   MTG_CUDA(h, cudaEventRecord(a.ev, stream));
   a.last = stream;
   a.used = true;
+  return MTG_OK;
+}
+
+// zeroed dynamic-tile counter of pipeline slot `slot`, ordered after the previous launch that used it
+int tile_counter_acquire(mtg_handle* h, int slot, cudaStream_t stream, unsigned long long** out) {
+  mtg_handle::Arena& a = h->counters[slot];
+  const int rc = arena_acquire(h, a, 256, stream);
+  if (rc != MTG_OK) return rc;
+  *out = reinterpret_cast<unsigned long long*>(a.p);
+  MTG_CUDA(h, cudaMemsetAsync(*out, 0, sizeof(unsigned long long), stream));
   return MTG_OK;
 }
 
@@ -733,9 +744,8 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
           // not small against a tile (C2 0.581 vs 0.529, C4 0.812 vs 0.797)  [profiles/r02_k1_variants.json]
           const int64_t tiles_per_warp = (B / 16) / std::max<int64_t>(1, blocks * 4);
           if (h->dynamic_tiles == 1 || (h->dynamic_tiles == 0 && tiles_per_warp >= 8 && p->K > kV4MaxK)) {
-            if (!h->tile_counters) MTG_CUDA(h, cudaMalloc(&h->tile_counters, sizeof(unsigned long long) * 32 * (mtg_handle::kPipe + 1)));
-            tl.tile_counter = h->tile_counters + 32 * slot;
-            MTG_CUDA(h, cudaMemsetAsync(tl.tile_counter, 0, sizeof(unsigned long long), stream));
+            const int rc_ctr = tile_counter_acquire(h, slot, stream, &tl.tile_counter);
+            if (rc_ctr != MTG_OK) return rc_ctr;
           }
           {
             const int rc_smem = ensure_dyn_smem(h, (const void*)launch_fn, best_smem);
@@ -749,6 +759,7 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
           launch_fn<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl, tmap);
           MTG_CUDA(h, cudaGetLastError());
           h->launches++;
+          if (tl.tile_counter != nullptr) return arena_release(h, h->counters[slot], stream);
           return MTG_OK;
         }
       }
@@ -800,9 +811,8 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
           const int64_t tiles_per_warp = ((B + 15) / 16) / std::max<int64_t>(1, int64_t(best_ctas) * h->sm_count * 4);
           const bool dyn = h->dynamic_tiles == 1 || (h->dynamic_tiles == 0 && tiles_per_warp >= 16);
           if (dyn && !per_tile) {
-            if (!h->tile_counters) MTG_CUDA(h, cudaMalloc(&h->tile_counters, sizeof(unsigned long long) * 32 * (mtg_handle::kPipe + 1)));
-            tl.tile_counter = h->tile_counters + 32 * slot;  // 256-byte apart
-            MTG_CUDA(h, cudaMemsetAsync(tl.tile_counter, 0, sizeof(unsigned long long), stream));
+            const int rc_ctr = tile_counter_acquire(h, slot, stream, &tl.tile_counter);
+            if (rc_ctr != MTG_OK) return rc_ctr;
           }
           {
         const int rc_smem = ensure_dyn_smem(h, (const void*)fn, size_t(best_smem));
@@ -818,6 +828,7 @@ int launch_solve(mtg_handle* h, const mtg_problem* p, CachedTopology* topo, int6
           fn<<<(unsigned)blocks, mtg::kTmemThreads, best_smem, stream>>>(prm, tl, tmap);
           MTG_CUDA(h, cudaGetLastError());
           h->launches++;
+          if (tl.tile_counter != nullptr) return arena_release(h, h->counters[slot], stream);
           return MTG_OK;
         }
       }
@@ -1029,9 +1040,8 @@ void mtg_destroy(mtg_handle* h) {
     cudaFree(t.d_slot_col);
     cudaFree(t.d_vcol);
   }
-  if (h->tile_counters) cudaFree(h->tile_counters);
   for (int i = 0; i <= mtg_handle::kPipe; ++i) {
-    for (mtg_handle::Arena* a : {&h->scratch[i], &h->pack[i]}) {
+    for (mtg_handle::Arena* a : {&h->scratch[i], &h->pack[i], &h->counters[i]}) {
       if (a->p) cudaFree(a->p);
       if (a->ev) cudaEventDestroy(a->ev);
     }

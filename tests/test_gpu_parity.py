@@ -692,3 +692,35 @@ def test_batched_evaluate_range_bitwise_vs_oracle(solver, oracle):
                     assert np.array_equal(out[b, :k, q, :], o_ref[:k]), (t0, b, der)
                     assert np.array_equal(st[b, :k], st_ref[:k])
                     assert not out[b, k:].any()
+
+
+def test_one_handle_two_caller_streams_dynamic_tiles(solver, oracle):
+    """Two large solves of one handle enqueued on two different caller streams: the persistent kernel's dynamic tile
+    counter is per handle slot, so the second launch must be ordered behind the first (event), not race on the counter --
+    both results equal the single-stream solve bit for bit."""
+    import torch
+    import mav_trajectory_generation_b200 as m
+    N, r, K, D, B = 10, 4, 16, 3, 180000 // 16 * 16
+    prob = m.Problem(N, r, K, D)
+    pos, times = oracle.make_waypoint_batch(K, D, 2048, base_seed=77)
+    dev = torch.device("cuda:0")
+    t_small = torch.from_numpy(times).to(dev)
+    f_small = torch.from_numpy(oracle.waypoint_d_fixed(N, pos)).to(dev)
+    idx_a = torch.arange(B, device=dev) % 2048
+    idx_b = (torch.arange(B, device=dev) * 7 + 3) % 2048
+    ta, fa = t_small[idx_a].contiguous(), f_small[idx_a].contiguous()
+    tb, fb = t_small[idx_b].contiguous(), f_small[idx_b].contiguous()
+    solver.set_option(m.capi.OPT_DYNAMIC_TILES, 1)
+    try:
+        want_a = solver.solve_linear(prob, ta, fa)
+        want_b = solver.solve_linear(prob, tb, fb)
+        out_a, out_b = torch.zeros_like(want_a), torch.zeros_like(want_b)
+        torch.cuda.synchronize()
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        for _ in range(3):
+            solver.solve_linear(prob, ta, fa, coeffs=out_a, stream=s1.cuda_stream)
+            solver.solve_linear(prob, tb, fb, coeffs=out_b, stream=s2.cuda_stream)
+        torch.cuda.synchronize()
+    finally:
+        solver.set_option(m.capi.OPT_DYNAMIC_TILES, 0)
+    assert torch.equal(out_a, want_a) and torch.equal(out_b, want_b)
