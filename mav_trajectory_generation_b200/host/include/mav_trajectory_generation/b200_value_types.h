@@ -322,6 +322,26 @@ class Trajectory {
   void evaluateRange(double t_start, double t_end, double dt, int derivative_order,
                      std::vector<Eigen::VectorXd>* result, std::vector<double>* sampling_times = nullptr) const;
 
+  // ---- re-shaping and vertex extraction (reference trajectory.h:86-124, src/trajectory.cpp:143-189, 238-343)
+  // One dimension of every segment as a 1-D trajectory.
+  Trajectory getTrajectoryWithSingleDimension(int dimension) const;
+  // This trajectory's dimensions followed by the other's (same number of segments, same segment times; the
+  // polynomial orders may differ, the shorter one is zero-padded by Segment::getSegmentWithAppendedDimension).
+  // An empty operand yields the other one.
+  bool getTrajectoryWithAppendedDimension(const Trajectory& trajectory_to_append, Trajectory* new_trajectory) const;
+  // This trajectory followed in time by the given ones (same D and N); false when a shape differs.
+  bool addTrajectories(const std::vector<Trajectory>& trajectories, Trajectory* merged) const;
+  // Adds A_r_B to the position polynomials' constant terms of every segment (at most the first 3 dimensions).
+  bool offsetTrajectory(const Eigen::VectorXd& A_r_B);
+  // Vertex carrying derivatives 0..max_derivative_order of the trajectory at time t / at its start / at its end.
+  Vertex getVertexAtTime(double t, int max_derivative_order) const;
+  Vertex getStartVertex(int max_derivative_order) const;
+  Vertex getGoalVertex(int max_derivative_order) const;
+  // The K+1 vertices at the segment boundaries; the 4-D overload splits position (dimensions 0..2) and yaw (3).
+  bool getVertices(int max_derivative_order, Vertex::Vector* vertices) const;
+  bool getVertices(int max_derivative_order_pos, int max_derivative_order_yaw, Vertex::Vector* pos_vertices,
+                   Vertex::Vector* yaw_vertices) const;
+
  private:
   int D_;
   int N_;

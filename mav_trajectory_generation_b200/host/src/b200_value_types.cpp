@@ -368,24 +368,39 @@ bool Segment::getSegmentWithAppendedDimension(const Segment& segment_to_append, 
     *new_segment = *this;
     return true;
   }
-  if (std::abs(time_ - segment_to_append.getTime()) > kNumSecPerNsec) return false;
-  const int new_N = N_ > segment_to_append.N() ? N_ : segment_to_append.N();
+  // Common order and duration (reference src/segment.cpp:201-262): the shorter-lived operand is re-parametrised to the
+  // longer duration (p(t) -> p(t * T_short / T_long)), the lower order is zero-padded.  (The reference applies the time
+  // scaling only when both orders are equal and silently drops it otherwise; here it is applied in both cases.)
+  const int new_N = std::max(N_, segment_to_append.N());
   const int new_D = D_ + segment_to_append.D();
+  const double new_time = std::max(time_, segment_to_append.getTime());
+  Segment mine = *this, other = segment_to_append;
+  if (new_time > 0.0) {
+    if (time_ < new_time)
+      for (int d = 0; d < D_; ++d) mine[d].scalePolynomialInTime(time_ / new_time);
+    else if (segment_to_append.getTime() < new_time)
+      for (int d = 0; d < other.D(); ++d) other[d].scalePolynomialInTime(segment_to_append.getTime() / new_time);
+  }
   *new_segment = Segment(new_N, new_D);
   bool ok = true;
   for (int i = 0; i < new_D; ++i) {
-    const Polynomial& src = i < D_ ? polynomials_[i] : segment_to_append[i - D_];
+    const Polynomial& src = i < D_ ? mine[i] : other[i - D_];
     Polynomial widened(new_N);
     ok = src.getPolynomialWithAppendedCoefficients(new_N, &widened) && ok;
     (*new_segment)[i] = widened;
   }
-  new_segment->setTime(time_);
+  new_segment->setTime(new_time);
   return ok;
 }
 
 bool Segment::offsetSegment(const Eigen::VectorXd& A_r_B) {
-  if (static_cast<int>(A_r_B.size()) < D_) return false;
-  for (int d = 0; d < D_; ++d) polynomials_[d].offsetPolynomial(A_r_B[d]);
+  // only the translational part moves (the first three dimensions at most), as in the reference (src/segment.cpp:264-276)
+  const int n = std::min(D_, 3);
+  if (static_cast<int>(A_r_B.size()) < n) {
+    LOG(WARNING) << "Offset vector size smaller than segment dimension.";
+    return false;
+  }
+  for (int d = 0; d < n; ++d) polynomials_[d].offsetPolynomial(A_r_B[d]);
   return true;
 }
 
@@ -445,6 +460,111 @@ Eigen::VectorXd Trajectory::evaluate(double t, int derivative_order) const {
     start -= segments_[i].getTime();
   }
   return segments_[i].evaluate(t - start, derivative_order);
+}
+
+Trajectory Trajectory::getTrajectoryWithSingleDimension(int dimension) const {
+  CHECK_LT(dimension, D_);
+  Segment::Vector picked;
+  picked.reserve(segments_.size());
+  for (const Segment& s : segments_) {
+    Segment one(N_, 1);
+    CHECK(s.getSegmentWithSingleDimension(dimension, &one));
+    picked.push_back(one);
+  }
+  Trajectory out;
+  if (!picked.empty()) out.setSegments(picked);
+  return out;
+}
+
+bool Trajectory::getTrajectoryWithAppendedDimension(const Trajectory& trajectory_to_append,
+                                                    Trajectory* new_trajectory) const {
+  CHECK_NOTNULL(new_trajectory);
+  if (N_ == 0 || D_ == 0) {  // nothing here yet: the result is the other trajectory
+    *new_trajectory = trajectory_to_append;
+    return true;
+  }
+  if (trajectory_to_append.N() == 0 || trajectory_to_append.D() == 0) {
+    *new_trajectory = *this;
+    return true;
+  }
+  CHECK_EQ(K(), trajectory_to_append.K());
+  Segment::Vector joined;
+  joined.reserve(segments_.size());
+  for (size_t k = 0; k < segments_.size(); ++k) {
+    Segment both(0, 0);
+    if (!segments_[k].getSegmentWithAppendedDimension(trajectory_to_append.segments()[k], &both)) return false;
+    joined.push_back(both);
+  }
+  new_trajectory->setSegments(joined);
+  return true;
+}
+
+bool Trajectory::addTrajectories(const std::vector<Trajectory>& trajectories, Trajectory* merged) const {
+  CHECK_NOTNULL(merged);
+  *merged = *this;
+  for (const Trajectory& t : trajectories) {
+    if (t.D() != D_ || t.N() != N_) {
+      LOG(WARNING) << "addTrajectories: shape (D, N) = (" << t.D() << ", " << t.N() << ") does not match (" << D_
+                   << ", " << N_ << ")";
+      return false;
+    }
+    merged->addSegments(t.segments());
+  }
+  return true;
+}
+
+bool Trajectory::offsetTrajectory(const Eigen::VectorXd& A_r_B) {
+  if (A_r_B.size() < std::min(D_, 3)) {
+    LOG(WARNING) << "Offset vector size smaller than trajectory dimension.";
+    return false;
+  }
+  for (Segment& s : segments_)
+    if (!s.offsetSegment(A_r_B)) return false;
+  return true;
+}
+
+Vertex Trajectory::getVertexAtTime(double t, int max_derivative_order) const {
+  Vertex v(D_);
+  for (int derivative = 0; derivative <= max_derivative_order; ++derivative)
+    v.addConstraint(derivative, evaluate(t, derivative));
+  return v;
+}
+
+Vertex Trajectory::getStartVertex(int max_derivative_order) const { return getVertexAtTime(0.0, max_derivative_order); }
+
+Vertex Trajectory::getGoalVertex(int max_derivative_order) const {
+  return getVertexAtTime(max_time_, max_derivative_order);
+}
+
+bool Trajectory::getVertices(int max_derivative_order, Vertex::Vector* vertices) const {
+  CHECK_NOTNULL(vertices);
+  vertices->assign(segments_.size() + 1, Vertex(D_));
+  vertices->front() = getStartVertex(max_derivative_order);
+  double t = 0.0;  // accumulated exactly like the reference: boundary k sits at the running sum of the segment times
+  for (size_t i = 0; i < segments_.size(); ++i) {
+    t += segments_[i].getTime();
+    (*vertices)[i + 1] = getVertexAtTime(t, max_derivative_order);
+  }
+  return true;
+}
+
+bool Trajectory::getVertices(int max_derivative_order_pos, int max_derivative_order_yaw, Vertex::Vector* pos_vertices,
+                             Vertex::Vector* yaw_vertices) const {
+  CHECK_NOTNULL(pos_vertices);
+  CHECK_NOTNULL(yaw_vertices);
+  const std::vector<size_t> pos_dims = {0, 1, 2};
+  const std::vector<size_t> yaw_dims = {3};
+  const int order = std::max(max_derivative_order_pos, max_derivative_order_yaw);
+  pos_vertices->assign(segments_.size() + 1, Vertex(3));
+  yaw_vertices->assign(segments_.size() + 1, Vertex(1));
+  double t = 0.0;
+  for (size_t i = 0; i <= segments_.size(); ++i) {
+    if (i > 0) t += segments_[i - 1].getTime();
+    const Vertex full = getVertexAtTime(t, order);
+    if (!full.getSubdimension(pos_dims, max_derivative_order_pos, &(*pos_vertices)[i])) return false;
+    if (!full.getSubdimension(yaw_dims, max_derivative_order_yaw, &(*yaw_vertices)[i])) return false;
+  }
+  return true;
 }
 
 void Trajectory::evaluateRange(double t_start, double t_end, double dt, int derivative_order,

@@ -321,6 +321,121 @@ static void testExtremaAndConversions() {
   }
 }
 
+// Trajectory re-shaping and vertex extraction (reference trajectory.h:86-124): pure host code, no GPU.
+static Trajectory randomTrajectory(int K, int D, int N, unsigned seed, const std::vector<double>& times) {
+  std::mt19937 gen(seed);
+  std::uniform_real_distribution<double> coef(-1.0, 1.0);
+  Segment::Vector segs;
+  for (int k = 0; k < K; ++k) {
+    Segment sgm(N, D);
+    for (int d = 0; d < D; ++d) {
+      Eigen::VectorXd c(N);
+      for (int j = 0; j < N; ++j) c[j] = coef(gen);
+      sgm[d] = Polynomial(N, c);
+    }
+    sgm.setTime(times[k]);
+    segs.push_back(sgm);
+  }
+  Trajectory t;
+  t.setSegments(segs);
+  return t;
+}
+
+static void testTrajectoryReshaping() {
+  const std::vector<double> times = {1.5, 0.75, 2.25};
+  const Trajectory full = randomTrajectory(3, 4, 6, 11, times);
+  const double probe[] = {0.0, 0.4, 1.5, 1.9, 2.25, 3.0, 4.5};
+  // single dimension keeps the segment times and the polynomial
+  for (int d = 0; d < 4; ++d) {
+    const Trajectory one = full.getTrajectoryWithSingleDimension(d);
+    EXPECT(one.D() == 1 && one.N() == 6 && one.K() == 3);
+    EXPECT_NEAR(one.getMaxTime(), full.getMaxTime(), 0.0);
+    for (double t : probe)
+      for (int der = 0; der < 3; ++der) EXPECT_NEAR(one.evaluate(t, der)[0], full.evaluate(t, der)[d], 0.0);
+  }
+  // position (dimensions 0..2) + yaw (dimension 3) re-assembled dimension by dimension equals the original
+  {
+    Trajectory acc;
+    for (int d = 0; d < 4; ++d) {
+      Trajectory next;
+      EXPECT(acc.getTrajectoryWithAppendedDimension(full.getTrajectoryWithSingleDimension(d), &next));
+      acc = next;
+    }
+    EXPECT(acc == full);
+    Trajectory same;
+    EXPECT(full.getTrajectoryWithAppendedDimension(Trajectory(), &same));
+    EXPECT(same == full);
+    // different polynomial orders: the result carries the larger one and still evaluates to both parts
+    const Trajectory low = randomTrajectory(3, 1, 4, 12, times);
+    Trajectory mixed;
+    EXPECT(full.getTrajectoryWithAppendedDimension(low, &mixed));
+    EXPECT(mixed.D() == 5 && mixed.N() == 6);
+    for (double t : probe) {
+      EXPECT_NEAR(mixed.evaluate(t, 1)[4], low.evaluate(t, 1)[0], 1e-15);
+      EXPECT_NEAR(mixed.evaluate(t, 0)[2], full.evaluate(t, 0)[2], 0.0);
+    }
+    // a shorter-lived segment of the appended trajectory is stretched to the longer duration (src/segment.cpp:218-231)
+    const Trajectory other_times = randomTrajectory(3, 1, 6, 13, {1.5, 0.5, 2.25});
+    Trajectory stretched;
+    EXPECT(full.getTrajectoryWithAppendedDimension(other_times, &stretched));
+    EXPECT_NEAR(stretched.getMaxTime(), full.getMaxTime(), 0.0);
+    EXPECT_NEAR(stretched.evaluate(1.5 + 0.75 * 0.4, 0)[4], other_times.evaluate(1.5 + 0.5 * 0.4, 0)[0], 1e-14);
+    EXPECT_NEAR(stretched.evaluate(1.5 + 0.75 * 0.4, 0)[1], full.evaluate(1.5 + 0.75 * 0.4, 0)[1], 0.0);
+  }
+  // concatenation in time
+  {
+    const Trajectory second = randomTrajectory(2, 4, 6, 14, {0.5, 1.25});
+    Trajectory merged;
+    EXPECT(full.addTrajectories({second}, &merged));
+    EXPECT(merged.K() == 5);
+    EXPECT_NEAR(merged.getMaxTime(), full.getMaxTime() + second.getMaxTime(), 1e-15);
+    EXPECT_NEAR(merged.evaluate(full.getMaxTime() + 0.3, 0)[1], second.evaluate(0.3, 0)[1], 1e-13);
+    EXPECT_NEAR(merged.evaluate(1.0, 2)[3], full.evaluate(1.0, 2)[3], 0.0);
+    Trajectory bad;
+    EXPECT(!full.addTrajectories({randomTrajectory(2, 3, 6, 15, {0.5, 1.25})}, &bad));
+  }
+  // offset: positions move, derivatives do not; too short an offset vector is refused
+  {
+    Trajectory moved = full;
+    Eigen::VectorXd off(3);
+    off[0] = 1.0; off[1] = -2.0; off[2] = 0.5;
+    EXPECT(moved.offsetTrajectory(off));
+    for (double t : probe) {
+      const Eigen::VectorXd a = moved.evaluate(t, 0), b = full.evaluate(t, 0);
+      for (int d = 0; d < 3; ++d) EXPECT_NEAR(a[d], b[d] + off[d], 1e-14);
+      EXPECT_NEAR(a[3], b[3], 0.0);
+      EXPECT_NEAR(moved.evaluate(t, 1)[1], full.evaluate(t, 1)[1], 0.0);
+    }
+    Eigen::VectorXd too_short(2);
+    too_short[0] = too_short[1] = 0.0;
+    EXPECT(!moved.offsetTrajectory(too_short));
+  }
+  // vertices at the segment boundaries
+  {
+    const Vertex v = full.getVertexAtTime(1.9, derivative_order::ACCELERATION);
+    EXPECT(v.D() == 4 && v.getNumberOfConstraints() == 3);
+    Eigen::VectorXd c;
+    EXPECT(v.getConstraint(derivative_order::VELOCITY, &c));
+    EXPECT_NEAR(c[2], full.evaluate(1.9, 1)[2], 0.0);
+    EXPECT(full.getStartVertex(1).isEqualTol(full.getVertexAtTime(0.0, 1), 0.0));
+    EXPECT(full.getGoalVertex(1).isEqualTol(full.getVertexAtTime(full.getMaxTime(), 1), 0.0));
+    Vertex::Vector all;
+    EXPECT(full.getVertices(derivative_order::JERK, &all));
+    EXPECT(all.size() == 4 && all[2].getNumberOfConstraints() == 4);
+    EXPECT(all[2].getConstraint(derivative_order::POSITION, &c));
+    EXPECT_NEAR(c[0], full.evaluate(1.5 + 0.75, 0)[0], 0.0);
+    Vertex::Vector pos, yaw;
+    EXPECT(full.getVertices(derivative_order::ACCELERATION, derivative_order::VELOCITY, &pos, &yaw));
+    EXPECT(pos.size() == 4 && yaw.size() == 4 && pos[1].D() == 3 && yaw[1].D() == 1);
+    EXPECT(pos[1].getNumberOfConstraints() == 3 && yaw[1].getNumberOfConstraints() == 2);
+    EXPECT(yaw[3].getConstraint(derivative_order::VELOCITY, &c));
+    EXPECT_NEAR(c[0], full.evaluate(full.getMaxTime(), 1)[3], 0.0);
+    // a 3-D trajectory has no yaw dimension to split off
+    Vertex::Vector p3, y3;
+    EXPECT(!randomTrajectory(2, 3, 6, 16, {1.0, 1.0}).getVertices(1, 1, &p3, &y3));
+  }
+}
+
 static void testLayoutOnly() {
   const Params& p = kParams[4];
   Vertex::Vector vertices = fixtureVertices(p);
@@ -580,6 +695,7 @@ int main(int argc, char** argv) {
   testLayoutOnly();
   testYamlIo();
   testExtremaAndConversions();
+  testTrajectoryReshaping();
   if (!cpu_only) {
     testTwoVerticesSetup();
     testReadmeExample();
