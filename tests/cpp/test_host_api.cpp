@@ -13,6 +13,7 @@
 #include "mav_trajectory_generation/batch_polynomial_optimization.h"
 #include "mav_trajectory_generation/io.h"
 #include "mav_trajectory_generation/polynomial_optimization_linear.h"
+#include "mav_trajectory_generation/trajectory_sampling.h"
 #include "mav_trajectory_generation_ros/ros_conversions.h"
 
 using namespace mav_trajectory_generation;
@@ -436,6 +437,109 @@ static void testTrajectoryReshaping() {
   }
 }
 
+// trajectory_sampling.h (reference src/trajectory_sampling.cpp): flat states of 3-, 4- and 6-dimensional trajectories.
+static void quatToMatrix(const mav_msgs::Quaternion& q, double R[3][3]) {
+  const double w = q.w, x = q.x, y = q.y, z = q.z;
+  R[0][0] = 1 - 2 * (y * y + z * z); R[0][1] = 2 * (x * y - w * z);     R[0][2] = 2 * (x * z + w * y);
+  R[1][0] = 2 * (x * y + w * z);     R[1][1] = 1 - 2 * (x * x + z * z); R[1][2] = 2 * (y * z - w * x);
+  R[2][0] = 2 * (x * z - w * y);     R[2][1] = 2 * (y * z + w * x);     R[2][2] = 1 - 2 * (x * x + y * y);
+}
+
+static void testTrajectorySampling() {
+  using mav_msgs::EigenTrajectoryPoint;
+  const std::vector<double> times = {1.5, 0.75, 2.25};
+  const Trajectory t4 = randomTrajectory(3, 4, 8, 21, times);
+  {
+    EigenTrajectoryPoint st;
+    const double ts = 1.9;
+    EXPECT(sampleTrajectoryAtTime(t4, ts, &st));
+    for (int d = 0; d < 3; ++d) {
+      EXPECT_NEAR(st.position_W[d], t4.evaluate(ts, 0)[d], 0.0);
+      EXPECT_NEAR(st.velocity_W[d], t4.evaluate(ts, 1)[d], 0.0);
+      EXPECT_NEAR(st.acceleration_W[d], t4.evaluate(ts, 2)[d], 0.0);
+      EXPECT_NEAR(st.jerk_W[d], t4.evaluate(ts, 3)[d], 0.0);
+      EXPECT_NEAR(st.snap_W[d], t4.evaluate(ts, 4)[d], 0.0);
+    }
+    const double yaw = t4.evaluate(ts, 0)[3];
+    EXPECT_NEAR(std::remainder(st.getYaw() - yaw, 2.0 * M_PI), 0.0, 1e-14);
+    EXPECT_NEAR(st.getYawRate(), t4.evaluate(ts, 1)[3], 0.0);
+    EXPECT_NEAR(st.getYawAcc(), t4.evaluate(ts, 2)[3], 0.0);
+    EXPECT(st.time_from_start_ns == static_cast<int64_t>(ts * 1e9));
+    EXPECT(st.degrees_of_freedom == mav_msgs::DOF4);
+    EXPECT(!sampleTrajectoryAtTime(t4, -0.1, &st));
+    EXPECT(!sampleTrajectoryAtTime(t4, t4.getMaxTime() + 0.1, &st));
+    EXPECT(!sampleTrajectoryAtTime(randomTrajectory(2, 2, 6, 22, {1.0, 1.0}), 0.5, &st));
+    EXPECT(sampleSegmentAtTime(t4.segments()[1], 0.3, &st));
+    EXPECT_NEAR(st.position_W[1], t4.segments()[1].evaluate(0.3, 0)[1], 0.0);
+    EXPECT(!sampleSegmentAtTime(t4.segments()[1], 0.8, &st));
+  }
+  {  // range: the sample set of evaluateRange, one state per sample
+    mav_msgs::EigenTrajectoryPointVector states, whole, by_duration;
+    const double dt = 0.11;
+    EXPECT(sampleTrajectoryInRange(t4, 0.4, 4.0, dt, &states));
+    std::vector<Eigen::VectorXd> pos, acc;
+    t4.evaluateRange(0.4, 4.0, dt, 0, &pos);
+    t4.evaluateRange(0.4, 4.0, dt, 2, &acc);
+    EXPECT(states.size() == pos.size() && !states.empty());
+    for (size_t i = 0; i < states.size(); i += 5) {
+      EXPECT_NEAR(states[i].position_W[2], pos[i][2], 0.0);
+      EXPECT_NEAR(states[i].acceleration_W[0], acc[i][0], 0.0);
+      EXPECT_NEAR(states[i].getYawAcc(), acc[i][3], 0.0);
+      EXPECT(states[i].time_from_start_ns == static_cast<int64_t>((0.4 + dt * i) * 1e9));
+    }
+    EXPECT(sampleWholeTrajectory(t4, dt, &whole));
+    EXPECT(sampleTrajectoryStartDuration(t4, 0.0, t4.getMaxTime(), dt, &by_duration));
+    EXPECT(whole.size() == by_duration.size() && whole.size() > states.size());
+    EXPECT(!sampleTrajectoryInRange(t4, 0.4, t4.getMaxTime() + 1.0, dt, &states));
+  }
+  {  // 6-D: rotation vector in the last three dimensions; angular rates against finite differences of the rotation
+    const Trajectory t6 = randomTrajectory(2, 6, 8, 23, {2.0, 1.5});
+    const double ts = 1.3, hstep = 1e-5;
+    EigenTrajectoryPoint s0, sp, sm;
+    EXPECT(sampleTrajectoryAtTime(t6, ts, &s0));
+    EXPECT(sampleTrajectoryAtTime(t6, ts + hstep, &sp));
+    EXPECT(sampleTrajectoryAtTime(t6, ts - hstep, &sm));
+    EXPECT(s0.degrees_of_freedom == mav_msgs::DOF6);
+    double R0[3][3], Rp[3][3], Rm[3][3], W[3][3];
+    quatToMatrix(s0.orientation_W_B, R0);
+    quatToMatrix(sp.orientation_W_B, Rp);
+    quatToMatrix(sm.orientation_W_B, Rm);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double acc = 0.0;
+        for (int k = 0; k < 3; ++k) acc += (Rp[i][k] - Rm[i][k]) / (2 * hstep) * R0[j][k];  // dR/dt R^T
+        W[i][j] = acc;
+      }
+    const double wn = std::sqrt(W[2][1] * W[2][1] + W[0][2] * W[0][2] + W[1][0] * W[1][0]);
+    const double fd_tol = 1e-6 * (1.0 + wn);  // central differences of a fast rotation: ~1e-8 relative
+    EXPECT_NEAR(s0.angular_velocity_W[0], W[2][1], fd_tol);
+    EXPECT_NEAR(s0.angular_velocity_W[1], W[0][2], fd_tol);
+    EXPECT_NEAR(s0.angular_velocity_W[2], W[1][0], fd_tol);
+    EXPECT_NEAR(W[0][0], 0.0, fd_tol);  // skew symmetric: the quaternion is a unit rotation
+    for (int d = 0; d < 3; ++d) {
+      const double fd = (sp.angular_velocity_W[d] - sm.angular_velocity_W[d]) / (2 * hstep);
+      EXPECT_NEAR(s0.angular_acceleration_W[d], fd, 1e-6 * (1.0 + std::abs(fd)));
+    }
+    // the rotation is the exponential of the sampled rotation vector: R phi = phi
+    const Eigen::VectorXd p = t6.evaluate(ts, 0);
+    for (int i = 0; i < 3; ++i)
+      EXPECT_NEAR(R0[i][0] * p[3] + R0[i][1] * p[4] + R0[i][2] * p[5], p[3 + i], 1e-14);
+    // near the zero rotation vector the series branch is used
+    Segment tiny(2, 6);
+    for (int d = 0; d < 6; ++d) {
+      Eigen::VectorXd c(2);
+      c[0] = d < 3 ? 1.0 : 1e-7 * (d - 2);
+      c[1] = 0.25 * (d + 1);
+      tiny[d] = Polynomial(2, c);
+    }
+    tiny.setTime(1.0);
+    EigenTrajectoryPoint sz;
+    EXPECT(sampleSegmentAtTime(tiny, 0.0, &sz));
+    EXPECT_NEAR(sz.angular_velocity_W[0], 1.0, 1e-6);  // phi ~ 0: omega = dphi = (1.0, 1.25, 1.5)
+    EXPECT_NEAR(sz.angular_velocity_W[2], 1.5, 1e-6);
+  }
+}
+
 static void testLayoutOnly() {
   const Params& p = kParams[4];
   Vertex::Vector vertices = fixtureVertices(p);
@@ -696,6 +800,7 @@ int main(int argc, char** argv) {
   testYamlIo();
   testExtremaAndConversions();
   testTrajectoryReshaping();
+  testTrajectorySampling();
   if (!cpu_only) {
     testTwoVerticesSetup();
     testReadmeExample();
