@@ -40,5 +40,13 @@ inline bool trajectoryFromFile(const std::string& filename, Trajectory* trajecto
   return true;
 }
 
+// Matlab-readable dump of the sampled flat states (reference src/io.cpp:221-279): the whole trajectory sampled every
+// 0.01 s, one row per sample, 27 columns
+//   [t_ns, x y z, vx vy vz, ax ay az, jx jy jz, sx sy sz, qw qx qy qz, wx wy wz, w'x w'y w'z, tm]
+// where column tm of row j (j < number of segments) holds the accumulated time at the end of segment j.  Text layout as
+// the reference's `fs << Eigen::MatrixXd`: 6 significant digits, single-space separated, columns right-aligned to the
+// widest entry.
+bool sampledTrajectoryStatesToFile(const std::string& filename, const Trajectory& trajectory);
+
 }  // namespace mav_trajectory_generation
 #endif

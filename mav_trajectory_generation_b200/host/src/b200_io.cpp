@@ -1,11 +1,14 @@
 // b200_io.cpp -- dependency-free writer / reader for the reference's segment YAML schema (see io.h).
 #include "mav_trajectory_generation/io.h"
+#include "mav_trajectory_generation/trajectory_sampling.h"
 
+#include <algorithm>
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <sstream>
+#include <vector>
 
 namespace mav_trajectory_generation {
 
@@ -173,6 +176,58 @@ bool segmentsFromFile(const std::string& filename, Segment::Vector* segments) {
   std::stringstream buffer;
   buffer << in.rdbuf();
   return segmentsFromYamlString(buffer.str(), segments);
+}
+
+bool sampledTrajectoryStatesToFile(const std::string& filename, const Trajectory& trajectory) {
+  const double sampling_time = 0.01;
+  mav_msgs::EigenTrajectoryPoint::Vector points;
+  if (!sampleWholeTrajectory(trajectory, sampling_time, &points)) return false;
+  const int dim = 3, cols = 8 * dim + 3;
+  std::vector<double> table(points.size() * size_t(cols), 0.0);
+  for (size_t i = 0; i < points.size(); ++i) {
+    const mav_msgs::EigenTrajectoryPoint& st = points[i];
+    double* row = &table[i * cols];
+    row[0] = static_cast<double>(st.time_from_start_ns);
+    for (int d = 0; d < dim; ++d) {
+      row[1 + d] = st.position_W[d];
+      row[1 + dim + d] = st.velocity_W[d];
+      row[1 + 2 * dim + d] = st.acceleration_W[d];
+      row[1 + 3 * dim + d] = st.jerk_W[d];
+      row[1 + 4 * dim + d] = st.snap_W[d];
+      row[2 + 6 * dim + d] = st.angular_velocity_W[d];
+      row[2 + 7 * dim + d] = st.angular_acceleration_W[d];
+    }
+    row[1 + 5 * dim] = st.orientation_W_B.w;
+    row[2 + 5 * dim] = st.orientation_W_B.x;
+    row[3 + 5 * dim] = st.orientation_W_B.y;
+    row[4 + 5 * dim] = st.orientation_W_B.z;
+  }
+  double accumulated = 0.0;  // end time of segment j in the last column of row j
+  for (size_t j = 0; j < trajectory.segments().size() && j < points.size(); ++j) {
+    accumulated += trajectory.segments()[j].getTime();
+    table[j * cols + (2 + 8 * dim)] = accumulated;
+  }
+  // text layout of an Eigen matrix streamed with the default format: %g-style 6 significant digits, one space between
+  // coefficients, every coefficient right-aligned to the widest one of the whole matrix
+  std::vector<std::string> cells(table.size());
+  size_t width = 0;
+  for (size_t k = 0; k < table.size(); ++k) {
+    std::ostringstream cell;
+    cell << table[k];
+    cells[k] = cell.str();
+    width = std::max(width, cells[k].size());
+  }
+  std::ofstream fs(filename);
+  if (!fs) return false;
+  for (size_t i = 0; i < points.size(); ++i) {
+    for (int c = 0; c < cols; ++c) {
+      const std::string& cell = cells[i * cols + c];
+      if (c) fs << ' ';
+      fs << std::string(width - cell.size(), ' ') << cell;
+    }
+    if (i + 1 < points.size()) fs << '\n';
+  }
+  return static_cast<bool>(fs);
 }
 
 }  // namespace mav_trajectory_generation

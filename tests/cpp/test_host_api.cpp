@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <sstream>
+#include <fstream>
 #include <random>
 #include <string>
 #include <vector>
@@ -491,6 +493,35 @@ static void testTrajectorySampling() {
     EXPECT(sampleTrajectoryStartDuration(t4, 0.0, t4.getMaxTime(), dt, &by_duration));
     EXPECT(whole.size() == by_duration.size() && whole.size() > states.size());
     EXPECT(!sampleTrajectoryInRange(t4, 0.4, t4.getMaxTime() + 1.0, dt, &states));
+  }
+  {  // Matlab dump of the sampled states (io.h): one row per 0.01 s sample, 27 aligned columns
+    const std::string path = "/tmp/mtg_sampled_states_test.txt";
+    EXPECT(sampledTrajectoryStatesToFile(path, t4));
+    std::ifstream fin(path);
+    std::string line;
+    size_t rows = 0;
+    double first_tm = -1.0, x_row10 = 0.0;
+    size_t line_len = 0;
+    while (std::getline(fin, line)) {
+      std::istringstream ls(line);
+      std::vector<double> vals;
+      double v;
+      while (ls >> v) vals.push_back(v);
+      EXPECT(vals.size() == 27);
+      if (rows == 0) {
+        first_tm = vals[26];
+        line_len = line.size();
+      }
+      EXPECT(line.size() == line_len);  // aligned columns
+      if (rows == 10) x_row10 = vals[1];
+      ++rows;
+    }
+    mav_msgs::EigenTrajectoryPointVector whole;
+    EXPECT(sampleWholeTrajectory(t4, 0.01, &whole));
+    EXPECT(rows == whole.size() && rows > 400);
+    EXPECT_NEAR(first_tm, 1.5, 1e-12);
+    EXPECT_NEAR(x_row10, whole[10].position_W[0], 1e-5 * (1.0 + std::abs(whole[10].position_W[0])));
+    std::remove(path.c_str());
   }
   {  // 6-D: rotation vector in the last three dimensions; angular rates against finite differences of the rotation
     const Trajectory t6 = randomTrajectory(2, 6, 8, 23, {2.0, 1.5});
